@@ -1,0 +1,18 @@
+// eigb200 -- internal stage interfaces (host-callable, all work issued on ctx().stream).
+#pragma once
+#include "common.cuh"
+
+namespace eigb200 {
+
+int set_option(const char* name, int value);
+int get_option(const char* name);
+
+struct Options {
+  int trd_nb = 64;      // tridiagonalization panel width (reference: 32, zheevd_gpu.F90:63)
+  int bt_nb = 128;      // back-transformation block (reference: 64, zheevd_gpu.F90:64)
+  int symv_tma = 1;     // stage symv/hemv tiles through TMA (cp.async.bulk.tensor) when alignment allows
+  int trd_coop = 1;     // persistent cooperative panel kernel (0: one launch per phase)
+};
+Options& opts();
+
+}  // namespace eigb200

@@ -1,0 +1,51 @@
+"""Device-side timing of individual kernels through the C ABI (CUDA events, warm-up, L2-sized inputs)."""
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from eigensolver_gpu_b200 import stages as S  # noqa: E402
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench_gemm():
+    for cplx in (False, True):
+        dt = torch.complex128 if cplx else torch.float64
+        fl = 8 if cplx else 2
+        for (ta, tb, m, n, k) in [("N", "N", 8192, 8192, 8192), ("N", "N", 4096, 4096, 128), ("N", "C", 8192, 8192, 64),
+                                  ("C", "N", 128, 8192, 8192), ("N", "N", 8192, 8192, 128), ("N", "N", 4096, 4096, 4096)]:
+            if cplx and m * n * k > 4096 ** 3 * 2:
+                m //= 2; n //= 2
+            a = torch.randn((k, m) if ta == "N" else (m, k), dtype=dt, device="cuda")
+            b = torch.randn((n, k) if tb == "N" else (k, n), dtype=dt, device="cuda")
+            c = torch.zeros((n, m), dtype=dt, device="cuda")
+            ms = timeit(lambda: S.gemm(ta, tb, 1.0, a, b, 0.0, c, m=m, n=n, k=k))
+            print(f"gemm {'z' if cplx else 'd'} {ta}{tb} {m}x{n}x{k}: {ms:.3f} ms  {fl*m*n*k/ms*1e-9:.2f} TFLOP/s", flush=True)
+        for (n, k) in [(8192, 64), (8192, 32), (4096, 64)]:
+            a = torch.randn((k, n), dtype=dt, device="cuda")
+            b = torch.randn((k, n), dtype=dt, device="cuda")
+            c = torch.zeros((n, n), dtype=dt, device="cuda")
+            ms = timeit(lambda: S.her2k(-1.0, a, b, 1.0, c))
+            byt = n * n * (16 if cplx else 8)
+            print(f"her2k {'z' if cplx else 'd'} n={n} k={k}: {ms:.3f} ms  {fl*n*n*k/ms*1e-9:.2f} TFLOP/s  {byt/ms*1e-6:.0f} GB/s(R+W tri)", flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm"]
+    for w in which:
+        globals()["bench_" + w]()
