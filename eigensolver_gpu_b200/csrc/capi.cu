@@ -51,4 +51,21 @@ int eigb200_zher2k(int n, int k, double alpha, const void* A, int lda, const voi
                               (double2*)C, ldc);
 }
 
+int eigb200_dsymv(int n, const double* A, int lda, const double* x, double* y) {
+  API_BEGIN();
+  return hemv_upper<double>(ctx().stream, n, A, lda, x, y);
+}
+int eigb200_zhemv(int n, const void* A, int lda, const void* x, void* y) {
+  API_BEGIN();
+  return hemv_upper<double2>(ctx().stream, n, (const double2*)A, lda, (const double2*)x, (double2*)y);
+}
+int eigb200_dsytrd(int n, double* A, int lda, double* d, double* e, double* tau) {
+  API_BEGIN();
+  return hetrd_upper<double>(ctx().stream, n, A, lda, d, e, tau);
+}
+int eigb200_zhetrd(int n, void* A, int lda, double* d, double* e, void* tau) {
+  API_BEGIN();
+  return hetrd_upper<double2>(ctx().stream, n, (double2*)A, lda, d, e, (double2*)tau);
+}
+
 }  // extern "C"

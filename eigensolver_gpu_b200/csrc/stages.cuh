@@ -15,4 +15,9 @@ struct Options {
 };
 Options& opts();
 
+// y = A x (A Hermitian, upper triangle read), deterministic tile reduction
+template <typename T> int hemv_upper(cudaStream_t s, int n, const T* A, int64_t lda, const T* x, T* y);
+// blocked tridiagonalization, UPLO='U'
+template <typename T> int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, T* tau);
+
 }  // namespace eigb200
