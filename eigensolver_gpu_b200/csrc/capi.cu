@@ -68,4 +68,12 @@ int eigb200_zhetrd(int n, void* A, int lda, double* d, double* e, void* tau) {
   return hetrd_upper<double2>(ctx().stream, n, (double2*)A, lda, d, e, (double2*)tau);
 }
 
+int eigb200_dstedc(int n, double* d, double* e, double* Q, int ldq) {
+  API_BEGIN();
+  size_t need = stedc_scratch_bytes(n);
+  void* scr = ctx_scratch(need);
+  if (!scr) return -1;
+  return stedc_device(ctx().stream, n, d, e, Q, ldq, scr, ctx().scratch_bytes);
+}
+
 }  // extern "C"

@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmParams<T> pv, const GemmP
         const int gn = n0 + wn0 + j * 8 + 2 * t + r;
         if (gn >= p.N) continue;
         if (p.mode == 1 && gm > gn) continue;
-        T* cp = p.C + gm + (int64_t)gn * p.ldc;
+        const int cn = p.colmap ? p.colmap[gn] : gn;
+        T* cp = p.C + gm + (int64_t)cn * p.ldc;
         if constexpr (!CPLX) {
           double v = alpha * acc[i][j][r];
           if (beta != 0.0) v += beta * (*cp);

@@ -24,6 +24,7 @@ struct GemmParams {
   double alpha, beta;
   int mode;                 // 0: full C, 1: upper triangle of C only (row <= col)
   int real_diag;            // complex + mode 1: force Im C(i,i) = 0
+  const int* colmap;        // optional: output column gn is stored at column colmap[gn] of C
 };
 
 // op(A)(m,k): AK=false -> A[m + k*lda] ('N');  AK=true -> A[k + m*lda] ('T'/'C', conj via sa=-1)

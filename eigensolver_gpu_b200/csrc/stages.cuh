@@ -20,4 +20,9 @@ template <typename T> int hemv_upper(cudaStream_t s, int n, const T* A, int64_t 
 // blocked tridiagonalization, UPLO='U'
 template <typename T> int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, T* tau);
 
+// tridiagonal divide & conquer on the device
+size_t stedc_scratch_bytes(int n);
+int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t ldq, void* scratch,
+                 size_t scratch_bytes);
+
 }  // namespace eigb200

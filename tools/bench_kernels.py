@@ -45,6 +45,45 @@ def bench_gemm():
             print(f"her2k {'z' if cplx else 'd'} n={n} k={k}: {ms:.3f} ms  {fl*n*n*k/ms*1e-9:.2f} TFLOP/s  {byt/ms*1e-6:.0f} GB/s(R+W tri)", flush=True)
 
 
+
+
+def bench_hemv():
+    for cplx in (False, True):
+        dt = torch.complex128 if cplx else torch.float64
+        es = 16 if cplx else 8
+        for n in (2048, 4096, 8192, 16384):
+            a = torch.randn((n, n), dtype=dt, device="cuda")
+            x = torch.randn(n, dtype=dt, device="cuda")
+            ms = timeit(lambda: S.hemv(a, x), reps=20)
+            byt = es * (n * (n + 1) / 2 + 3 * n)
+            print(f"hemv {'z' if cplx else 'd'} n={n}: {ms*1e3:.1f} us  {byt/ms*1e-6:.0f} GB/s", flush=True)
+
+
+def bench_hetrd():
+    from eigensolver_gpu_b200._lib import load
+    lib = load()
+    for cplx, n in ((False, 2048), (False, 4096), (True, 4096), (True, 8192), (False, 8192)):
+        dt = torch.complex128 if cplx else torch.float64
+        g = torch.randn((n, n), dtype=dt, device="cuda")
+        a0 = g + g.conj().T
+        for nb, coop in ((64, 1), (32, 1), (64, 0)):
+            lib.eigb200_set_option(b"trd_nb", nb)
+            lib.eigb200_set_option(b"trd_coop", coop)
+            a = a0.clone()
+            S.hetrd(a)
+            a = a0.clone()
+            torch.cuda.synchronize()
+            t0 = time.time()
+            S.hetrd(a)
+            torch.cuda.synchronize()
+            dt_s = time.time() - t0
+            k = 4 if cplx else 1
+            print(f"hetrd {'z' if cplx else 'd'} n={n} nb={nb} coop={coop}: {dt_s*1e3:.1f} ms  {k*4/3*n**3/dt_s*1e-12:.2f} TFLOP/s "
+                  f"(hemv bytes {(16 if cplx else 8)*n**3/6/dt_s*1e-9:.0f} GB/s-equiv)", flush=True)
+        lib.eigb200_set_option(b"trd_nb", 64)
+        lib.eigb200_set_option(b"trd_coop", 1)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm"]
     for w in which:
