@@ -1,0 +1,122 @@
+"""Host-side mirror of the reference's Fortran interface (same names, argument order and meaning).
+
+    dsygvdx_gpu(N, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, work_h, lwork_h, iwork_h, liwork_h,
+                Z_h, ldz_h, w_h, _skip_host_copy=False) -> info         lib_eigsolve/dsygvdx_gpu.F90:71-72
+    zhegvdx_gpu(N, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, rwork, lrwork, work_h, lwork_h, rwork_h,
+                lrwork_h, iwork_h, liwork_h, Z_h, ldz_h, w_h, _skip_host_copy=False) -> info
+                                                                        lib_eigsolve/zhegvdx_gpu.F90:75-76
+
+Device arrays (A, B, Z, w, work, rwork) are CUDA torch tensors holding column-major data (see
+stages.to_dev); host arrays (*_h) are pinned CPU torch tensors or numpy arrays.  `info` is returned (0 ok,
+-1 error, as in the reference).  All compute happens in lib/libeigb200.so; there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import load
+from . import stages as S
+
+
+def init_eigsolve_gpu():
+    """eigsolve_vars.F90:39-59"""
+    return load().eigb200_init()
+
+
+def _dp(t):
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    return C.c_void_p(t.data_ptr())
+
+
+def _sync_stream():
+    lib = load()
+    lib.eigb200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+
+def dsygvdx_gpu(N, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, work_h, lwork_h, iwork_h, liwork_h, Z_h, ldz_h, w_h,
+                _skip_host_copy=False):
+    lib = load()
+    _sync_stream()
+    info = C.c_int(0)
+    lib.eigb200_dsygvdx(N, _dp(A), lda, _dp(B), ldb, _dp(Z), ldz, il, iu, _dp(w), _dp(work), lwork, _dp(work_h), lwork_h,
+                        _dp(iwork_h), liwork_h, _dp(Z_h), ldz_h, _dp(w_h), C.byref(info), 1 if _skip_host_copy else 0)
+    return info.value
+
+
+def zhegvdx_gpu(N, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, rwork, lrwork, work_h, lwork_h, rwork_h, lrwork_h,
+                iwork_h, liwork_h, Z_h, ldz_h, w_h, _skip_host_copy=False):
+    lib = load()
+    _sync_stream()
+    info = C.c_int(0)
+    lib.eigb200_zhegvdx(N, _dp(A), lda, _dp(B), ldb, _dp(Z), ldz, il, iu, _dp(w), _dp(work), lwork, _dp(rwork), lrwork,
+                        _dp(work_h), lwork_h, _dp(rwork_h), lrwork_h, _dp(iwork_h), liwork_h, _dp(Z_h), ldz_h, _dp(w_h),
+                        C.byref(info), 1 if _skip_host_copy else 0)
+    return info.value
+
+
+def dsyevd_gpu(jobz, uplo, il, iu, N, A, lda, Z, ldz, w, work, lwork, work_h, lwork_h, iwork_h, liwork_h, Z_h, ldz_h, w_h):
+    """dsyevd_gpu.F90:32-33 (jobz='V', uplo='U' only, as in the reference)."""
+    if jobz != "V" or uplo != "U":
+        print("Provided itype/uplo not supported!")      # dsyevd_gpu.F90:58-61
+        return 0
+    lib = load()
+    _sync_stream()
+    info = C.c_int(0)
+    lib.eigb200_dsyevd(il, iu, N, _dp(A), lda, _dp(Z), ldz, _dp(w), _dp(work), lwork, _dp(work_h), lwork_h, _dp(iwork_h),
+                       liwork_h, _dp(Z_h), ldz_h, _dp(w_h), C.byref(info))
+    return info.value
+
+
+def zheevd_gpu(jobz, uplo, il, iu, N, A, lda, Z, ldz, w, work, lwork, rwork, lrwork, work_h, lwork_h, rwork_h, lrwork_h,
+               iwork_h, liwork_h, Z_h, ldz_h, w_h):
+    """zheevd_gpu.F90:32-33."""
+    if jobz != "V" or uplo != "U":
+        print("Provided itype/uplo not supported!")      # zheevd_gpu.F90:58-61
+        return 0
+    lib = load()
+    _sync_stream()
+    info = C.c_int(0)
+    lib.eigb200_zheevd(il, iu, N, _dp(A), lda, _dp(Z), ldz, _dp(w), _dp(work), lwork, _dp(rwork), lrwork, _dp(work_h),
+                       lwork_h, _dp(rwork_h), lrwork_h, _dp(iwork_h), liwork_h, _dp(Z_h), ldz_h, _dp(w_h), C.byref(info))
+    return info.value
+
+
+class Workspace:
+    """Buffers sized by the reference's formulas (test_driver/test_zhegvdx.F90:266-290, test_dsygvdx.F90:292-314)."""
+
+    def __init__(self, n, cplx, device="cuda", host_z=True, pinned=True):
+        self.n, self.cplx = n, cplx
+        dt = torch.complex128 if cplx else torch.float64
+        self.lwork = 2 * 64 * 64 + (65 if cplx else 66) * n
+        self.work = torch.empty(self.lwork, dtype=dt, device=device)
+        self.lrwork = n
+        self.rwork = torch.empty(max(n, 1), dtype=torch.float64, device=device) if cplx else None
+        self.w = torch.empty(max(n, 1), dtype=torch.float64, device=device)
+        self.Z = torch.empty((n, n), dtype=dt, device=device)
+        # host workspaces: only their declared lengths matter (the device D&C does not use them); keep them
+        # tiny but report the reference minima so that the reference's size checks pass.
+        self.lwork_h = n if cplx else 1 + 6 * n + 2 * n * n
+        self.lrwork_h = 1 + 5 * n + 2 * n * n
+        self.liwork_h = 3 + 5 * n
+        pin = pinned and torch.cuda.is_available()
+        self.w_h = torch.empty(max(n, 1), dtype=torch.float64, pin_memory=pin)
+        self.Z_h = torch.empty((n, n), dtype=dt, pin_memory=pin) if host_z else None
+
+
+def solve_generalized(a_dev, b_dev, il, iu, ws=None, skip_host_copy=True):
+    """Convenience wrapper: A,B device tensors (column-major, upper triangles used; both overwritten).
+    Returns (info, w_dev[all n], Z_dev view of the first m columns (as (m, n) tensor), ws)."""
+    n = a_dev.shape[0]
+    cplx = a_dev.dtype == torch.complex128
+    ws = ws or Workspace(n, cplx, device=a_dev.device, host_z=not skip_host_copy)
+    if cplx:
+        info = zhegvdx_gpu(n, a_dev, n, b_dev, n, ws.Z, n, il, iu, ws.w, ws.work, ws.lwork, ws.rwork, ws.lrwork, None,
+                           ws.lwork_h, None, ws.lrwork_h, None, ws.liwork_h, ws.Z_h, n, ws.w_h, skip_host_copy)
+    else:
+        info = dsygvdx_gpu(n, a_dev, n, b_dev, n, ws.Z, n, il, iu, ws.w, ws.work, ws.lwork, None, ws.lwork_h, None,
+                           ws.liwork_h, ws.Z_h, n, ws.w_h, skip_host_copy)
+    return info, ws.w, ws.Z[: iu - il + 1], ws

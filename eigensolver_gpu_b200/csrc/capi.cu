@@ -76,4 +76,91 @@ int eigb200_dstedc(int n, double* d, double* e, double* Q, int ldq) {
   return stedc_device(ctx().stream, n, d, e, Q, ldq, scr, ctx().scratch_bytes);
 }
 
+int eigb200_dpotrf(int n, double* B, int ldb, int* info_h) {
+  API_BEGIN();
+  return potrf_upper<double>(ctx().stream, n, B, ldb, info_h);
+}
+int eigb200_zpotrf(int n, void* B, int ldb, int* info_h) {
+  API_BEGIN();
+  return potrf_upper<double2>(ctx().stream, n, (double2*)B, ldb, info_h);
+}
+int eigb200_dsygst(int n, double* A, int lda, const double* U, int ldu) {
+  API_BEGIN();
+  return hegst_upper<double>(ctx().stream, n, A, lda, U, ldu, (double*)nullptr, 0);
+}
+int eigb200_zhegst(int n, void* A, int lda, const void* U, int ldu) {
+  API_BEGIN();
+  return hegst_upper<double2>(ctx().stream, n, (double2*)A, lda, (const double2*)U, ldu, (double2*)nullptr, 0);
+}
+int eigb200_dtrsm(char side, char trans, int m, int n, const double* U, int ldu, double* B, int ldb) {
+  API_BEGIN();
+  return trsm_upper<double>(ctx().stream, side, trans == 'T' ? 'C' : trans, m, n, U, ldu, B, ldb);
+}
+int eigb200_ztrsm(char side, char trans, int m, int n, const void* U, int ldu, void* B, int ldb) {
+  API_BEGIN();
+  return trsm_upper<double2>(ctx().stream, side, trans, m, n, (const double2*)U, ldu, (double2*)B, ldb);
+}
+int eigb200_dormtr(int n, int m, const double* A, int lda, const double* tau, double* Z, int ldz) {
+  API_BEGIN();
+  void* scr = ctx_scratch(ormtr_scratch_bytes(n, m, sizeof(double)));
+  if (!scr) return -1;
+  return ormtr_upper<double>(ctx().stream, n, m, A, lda, tau, Z, ldz, scr, ctx().scratch_bytes);
+}
+int eigb200_zunmtr(int n, int m, const void* A, int lda, const void* tau, void* Z, int ldz) {
+  API_BEGIN();
+  void* scr = ctx_scratch(ormtr_scratch_bytes(n, m, sizeof(double2)));
+  if (!scr) return -1;
+  return ormtr_upper<double2>(ctx().stream, n, m, (const double2*)A, lda, (const double2*)tau, (double2*)Z, ldz, scr,
+                              ctx().scratch_bytes);
+}
+int64_t eigb200_scratch_bytes(int n, int is_complex) {
+  size_t es = is_complex ? 16 : 8;
+  size_t a = (size_t)n * n * 8 + 256 + stedc_scratch_bytes(n);
+  size_t b = ormtr_scratch_bytes(n, n, (int)es);
+  size_t c = ((size_t)n * n / 16 + (size_t)n * 200) * es + (1 << 20);
+  size_t r = a > b ? a : b;
+  return (int64_t)(r > c ? r : c);
+}
+
+int eigb200_dsygvdx(int n, double* A, int lda, double* B, int ldb, double* Z, int ldz, int il, int iu, double* w,
+                    double* work, int lwork, double* work_h, int lwork_h, int* iwork_h, int liwork_h, double* Z_h,
+                    int ldz_h, double* w_h, int* info, int skip_host_copy) {
+  (void)work_h; (void)iwork_h;
+  int dummy = 0;
+  if (!info) info = &dummy;
+  if (ctx_init() != 0) { *info = -1; return -1; }
+  return hegvdx_driver<double>(n, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, nullptr, 0, lwork_h, 0, liwork_h, Z_h,
+                               ldz_h, w_h, info, skip_host_copy);
+}
+int eigb200_zhegvdx(int n, void* A, int lda, void* B, int ldb, void* Z, int ldz, int il, int iu, double* w, void* work,
+                    int lwork, double* rwork, int lrwork, void* work_h, int lwork_h, double* rwork_h, int lrwork_h,
+                    int* iwork_h, int liwork_h, void* Z_h, int ldz_h, double* w_h, int* info, int skip_host_copy) {
+  (void)work_h; (void)rwork_h; (void)iwork_h;
+  int dummy = 0;
+  if (!info) info = &dummy;
+  if (ctx_init() != 0) { *info = -1; return -1; }
+  return hegvdx_driver<double2>(n, (double2*)A, lda, (double2*)B, ldb, (double2*)Z, ldz, il, iu, w, (double2*)work,
+                                lwork, rwork, lrwork, lwork_h, lrwork_h, liwork_h, (double2*)Z_h, ldz_h, w_h, info,
+                                skip_host_copy);
+}
+int eigb200_dsyevd(int il, int iu, int n, double* A, int lda, double* Z, int ldz, double* w, double* work, int lwork,
+                   double* work_h, int lwork_h, int* iwork_h, int liwork_h, double* Z_h, int ldz_h, double* w_h,
+                   int* info) {
+  (void)work_h; (void)lwork_h; (void)iwork_h; (void)liwork_h;
+  int dummy = 0;
+  if (!info) info = &dummy;
+  if (ctx_init() != 0) { *info = -1; return -1; }
+  return heevd_driver<double>(il, iu, n, A, lda, Z, ldz, w, work, lwork, nullptr, 0, Z_h, ldz_h, w_h, info);
+}
+int eigb200_zheevd(int il, int iu, int n, void* A, int lda, void* Z, int ldz, double* w, void* work, int lwork,
+                   double* rwork, int lrwork, void* work_h, int lwork_h, double* rwork_h, int lrwork_h, int* iwork_h,
+                   int liwork_h, void* Z_h, int ldz_h, double* w_h, int* info) {
+  (void)work_h; (void)lwork_h; (void)rwork_h; (void)lrwork_h; (void)iwork_h; (void)liwork_h;
+  int dummy = 0;
+  if (!info) info = &dummy;
+  if (ctx_init() != 0) { *info = -1; return -1; }
+  return heevd_driver<double2>(il, iu, n, (double2*)A, lda, (double2*)Z, ldz, w, (double2*)work, lwork, rwork, lrwork,
+                               (double2*)Z_h, ldz_h, w_h, info);
+}
+
 }  // extern "C"

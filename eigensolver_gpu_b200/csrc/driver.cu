@@ -1,0 +1,167 @@
+// eigb200 -- generalized and standard drivers behind the C ABI.
+//
+// dsygvdx_gpu / zhegvdx_gpu (dsygvdx_gpu.F90:71-168, zhegvdx_gpu.F90:75-182) and dsyevd_gpu / zheevd_gpu
+// (dsyevd_gpu.F90:32-132, zheevd_gpu.F90:32-134) re-built on the sm_100a stages of this library:
+//   potrf(B) -> [save tril(A) in Z] -> hegst -> hetrd -> [restore tril(A)] -> stedc ON DEVICE -> select il..iu
+//   -> back-transform -> trsm with U -> copies to the host buffers.
+// Same argument lists, workspace checks and info convention as the reference; the host workspaces are
+// accepted (and size-checked, so that a caller sized for the reference keeps working) but unused because the
+// divide and conquer no longer runs on the CPU.
+#include "common.cuh"
+#include "gemm.cuh"
+#include "stages.cuh"
+
+namespace eigb200 {
+
+namespace {
+
+template <typename T>
+__global__ void select_columns_kernel(const double* __restrict__ Q, int64_t ldq, int n, int c0, int m, T* Z,
+                                      int64_t ldz) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (r < n && c < m) Z[r + (int64_t)c * ldz] = from_real<T>(Q[r + (int64_t)(c0 + c) * ldq]);
+}
+
+}  // namespace
+
+// Standard problem on device data: A (upper) -> w(all n, ascending), Z(:, 0:m) eigenvectors il..iu (1-based).
+// d_e, d_tau: device workspaces of n doubles / n T.
+template <typename T>
+int heevd_core(cudaStream_t s, int n, int il, int iu, T* A, int64_t lda, T* Z, int64_t ldz, double* w, double* d_e,
+               T* d_tau, const T* restore_from, int64_t ld_restore) {
+  const int m = iu - il + 1;
+  if (hetrd_upper<T>(s, n, A, lda, w, d_e, d_tau) != 0) return -1;
+  if (restore_from) {
+    if (restore_lower<T>(s, n, A, lda, restore_from, ld_restore) != 0) return -1;
+  }
+  size_t nn = (size_t)n * n * sizeof(double);
+  size_t need_dc = nn + 256 + stedc_scratch_bytes(n);
+  size_t need_bt = ormtr_scratch_bytes(n, m, sizeof(T));
+  size_t need = need_dc > need_bt ? need_dc : need_bt;
+  char* scr = (char*)ctx_scratch(need);
+  if (!scr) return -1;
+  double* Qt = (double*)scr;
+  if (stedc_device(s, n, w, d_e, Qt, n, scr + ((nn + 255) & ~size_t(255)), ctx().scratch_bytes - ((nn + 255) & ~size_t(255))) != 0)
+    return -1;
+  select_columns_kernel<T><<<dim3(cdiv(n, 256), m), 256, 0, s>>>(Qt, n, n, il - 1, m, Z, ldz);
+  EIGB_LAUNCH_CHECK();
+  if (ormtr_upper<T>(s, n, m, A, lda, d_tau, Z, ldz, scr, ctx().scratch_bytes) != 0) return -1;
+  return 0;
+}
+
+template <typename T>
+int copy_results_to_host(cudaStream_t s, int n, int m, const T* Z, int64_t ldz, const double* w, T* Z_h, int64_t ldz_h,
+                         double* w_h, bool skip_z) {
+  if (w_h) EIGB_CUDA_CHECK(cudaMemcpyAsync(w_h, w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (!skip_z && Z_h) {
+    EIGB_CUDA_CHECK(cudaMemcpy2DAsync(Z_h, (size_t)ldz_h * sizeof(T), Z, (size_t)ldz * sizeof(T), (size_t)n * sizeof(T),
+                                      m, cudaMemcpyDeviceToHost, s));
+  }
+  EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+template <typename T>
+int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, int iu, double* w, T* work, int lwork,
+                  double* rwork, int lrwork, int lwork_h, int lrwork_h, int liwork_h, T* Z_h, int ldz_h, double* w_h,
+                  int* info, int skip_host_copy) {
+  const bool cplx = is_cplx<T>::value;
+  *info = 0;
+  const char* name = cplx ? "zhegvdx_gpu" : "dsygvdx_gpu";
+  const int64_t N = n;
+  // workspace checks: zhegvdx_gpu.F90:106-127 / dsygvdx_gpu.F90:100-113 (64-bit arithmetic: the reference's
+  // 1+5N+2N*N overflows default integers at N >= 32767)
+  const char* msg = nullptr;
+  if (cplx) {
+    if (lwork < 2 * 64 * 64 + 65 * N) msg = "lwork must be at least 2*64*64 + 65*N";
+    else if (lrwork < N) msg = "lrwork must be at least N";
+    else if (lwork_h < N) msg = "lwork_h must be at least N";
+    else if (lrwork_h >= 0 && lrwork_h < 1 + 5 * N + 2 * N * N && 1 + 5 * N + 2 * N * N <= 2147483647LL)
+      msg = "lrwork_h must be at least 1 + 5*N + 2*N*N";
+    else if (liwork_h < N) msg = "liwork_h must be at least 3 + 5*N";
+  } else {
+    if (lwork < 2 * 64 * 64 + 66 * N) msg = "lwork must be at least 2*64*64 + 66*N";
+    else if (lwork_h >= 0 && lwork_h < 1 + 6 * N + 2 * N * N && 1 + 6 * N + 2 * N * N <= 2147483647LL)
+      msg = "lwork_h must be at least 1 + 6*N + 2*N*N";
+    else if (liwork_h < N) msg = "liwork_h must be at least 3 + 5*N";
+  }
+  if (!msg && (n < 0 || lda < n || ldb < n || ldz < n)) msg = "N, lda, ldb, ldz inconsistent";
+  if (!msg && n > 0 && (il < 1 || iu > n || il > iu)) msg = "need 1 <= il <= iu <= N";
+  if (msg) {
+    printf(" %s error: %s\n", name, msg);
+    set_last_error("%s error: %s", name, msg);
+    *info = -1;
+    return -1;
+  }
+  if (n == 0) return 0;
+  cudaStream_t s = ctx().stream;
+  const int m = iu - il + 1;
+  int pinfo = 0;
+  if (potrf_upper<T>(s, n, B, ldb, &pinfo) != 0 || pinfo != 0) {
+    printf(" %s error: potrf failed!\n", name);
+    if (pinfo != 0) set_last_error("%s error: potrf failed (B not positive definite at pivot %d)", name, pinfo);
+    *info = -1;
+    return -1;
+  }
+  // tril(A) -> Z, A <- U^-H A U^-1 (zhegvdx_gpu.F90:145-158)
+  if (hegst_upper<T>(s, n, A, lda, B, ldb, Z, ldz) != 0) { *info = -1; return -1; }
+  double* d_e = cplx ? rwork : reinterpret_cast<double*>(work);
+  T* d_tau = cplx ? work : work + n;
+  // the strict lower triangle of A is restored from Z before Z is overwritten (zheevd_gpu.F90:89-96); Z is
+  // needed as the save area until then, so the restore happens inside heevd_core right after hetrd.
+  if (heevd_core<T>(s, n, il, iu, A, lda, Z, ldz, w, d_e, d_tau, Z, ldz) != 0) {
+    printf(" %s error: eigensolver stage failed: %s\n", name, "see eigb200_last_error()");
+    *info = -1;
+    return -1;
+  }
+  // eigenvectors of the generalized problem: Z <- U^-1 Z (zhegvdx_gpu.F90:169)
+  if (trsm_upper<T>(s, 'L', 'N', n, m, B, ldb, Z, ldz) != 0) { *info = -1; return -1; }
+  if (copy_results_to_host<T>(s, n, m, Z, ldz, w, Z_h, ldz_h, w_h, skip_host_copy != 0) != 0) {
+    printf(" %s error: copy to host failed!\n", name);
+    *info = -1;
+    return -1;
+  }
+  return 0;
+}
+
+template <typename T>
+int heevd_driver(int il, int iu, int n, T* A, int lda, T* Z, int ldz, double* w, T* work, int lwork, double* rwork,
+                 int lrwork, T* Z_h, int ldz_h, double* w_h, int* info) {
+  const bool cplx = is_cplx<T>::value;
+  *info = 0;
+  const int64_t N = n;
+  const char* name = cplx ? "zheevd_gpu" : "dsyevd_gpu";
+  const char* msg = nullptr;
+  if (cplx) {
+    if (lwork < 2 * 64 * 64 + 65 * N) msg = "lwork must be at least 2*64*64 + 65*N";
+    else if (lrwork < N) msg = "lrwork must be at least N";
+  } else {
+    if (lwork < 2 * 64 * 64 + 66 * N) msg = "lwork must be at least 2*64*64 + 66*N";
+  }
+  if (!msg && (n < 0 || lda < n || ldz < n)) msg = "N, lda, ldz inconsistent";
+  if (!msg && n > 0 && (il < 1 || iu > n || il > iu)) msg = "need 1 <= il <= iu <= N";
+  if (msg) {
+    printf(" %s error: %s\n", name, msg);
+    set_last_error("%s error: %s", name, msg);
+    *info = -1;
+    return -1;
+  }
+  if (n == 0) return 0;
+  cudaStream_t s = ctx().stream;
+  double* d_e = cplx ? rwork : reinterpret_cast<double*>(work);
+  T* d_tau = cplx ? work : work + n;
+  if (heevd_core<T>(s, n, il, iu, A, lda, Z, ldz, w, d_e, d_tau, (const T*)nullptr, 0) != 0) { *info = -1; return -1; }
+  if (copy_results_to_host<T>(s, n, iu - il + 1, Z, ldz, w, Z_h, ldz_h, w_h, false) != 0) { *info = -1; return -1; }
+  return 0;
+}
+
+template int hegvdx_driver<double>(int, double*, int, double*, int, double*, int, int, int, double*, double*, int,
+                                   double*, int, int, int, int, double*, int, double*, int*, int);
+template int hegvdx_driver<double2>(int, double2*, int, double2*, int, double2*, int, int, int, double*, double2*, int,
+                                    double*, int, int, int, int, double2*, int, double*, int*, int);
+template int heevd_driver<double>(int, int, int, double*, int, double*, int, double*, double*, int, double*, int,
+                                  double*, int, double*, int*);
+template int heevd_driver<double2>(int, int, int, double2*, int, double2*, int, double*, double2*, int, double*, int,
+                                   double2*, int, double*, int*);
+
+}  // namespace eigb200

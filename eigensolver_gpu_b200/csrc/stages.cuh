@@ -25,4 +25,26 @@ size_t stedc_scratch_bytes(int n);
 int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t ldq, void* scratch,
                  size_t scratch_bytes);
 
+// Cholesky / triangular solves / reduction to standard form (trsm.cu)
+template <typename T> int symmetrize_from_upper(cudaStream_t s, int n, T* A, int64_t lda, T* save, int64_t lds);
+template <typename T> int restore_lower(cudaStream_t s, int n, T* A, int64_t lda, const T* save, int64_t lds);
+template <typename T> int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h);
+template <typename T>
+int trsm_upper(cudaStream_t s, char side, char trans, int m, int n, const T* U, int64_t ldu, T* B, int64_t ldb);
+template <typename T>
+int hegst_upper(cudaStream_t s, int n, T* A, int64_t lda, const T* U, int64_t ldu, T* save, int64_t lds);
+// back-transformation (ormtr.cu)
+size_t ormtr_scratch_bytes(int n, int m, int esize);
+template <typename T>
+int ormtr_upper(cudaStream_t s, int n, int m, const T* A, int64_t lda, const T* tau, T* Z, int64_t ldz, void* scratch,
+                size_t scratch_bytes);
+// drivers (driver.cu)
+template <typename T>
+int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, int iu, double* w, T* work, int lwork,
+                  double* rwork, int lrwork, int lwork_h, int lrwork_h, int liwork_h, T* Z_h, int ldz_h, double* w_h,
+                  int* info, int skip_host_copy);
+template <typename T>
+int heevd_driver(int il, int iu, int n, T* A, int lda, T* Z, int ldz, double* w, T* work, int lwork, double* rwork,
+                 int lrwork, T* Z_h, int ldz_h, double* w_h, int* info);
+
 }  // namespace eigb200
