@@ -25,6 +25,10 @@ const char* eigb200_last_error(void) { return last_error(); }
 int eigb200_set_stream(void* s) { ctx().stream = (cudaStream_t)s; return 0; }
 int eigb200_version(void) { return 100; }
 
+int eigb200_prof_enable(int on) { prof_enable(on); return 0; }
+int eigb200_prof_reset(void) { prof_reset(); return 0; }
+int eigb200_prof_collect(double* ms, int* cnt, long long* launches) { prof_collect(ms, cnt, launches); return 0; }
+
 int eigb200_set_option(const char* name, int value) { return set_option(name, value); }
 int eigb200_get_option(const char* name) { return get_option(name); }
 

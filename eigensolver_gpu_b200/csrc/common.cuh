@@ -76,7 +76,7 @@ void set_last_error(const char* fmt, ...);
       return -1;                                                                              \
     }                                                                                         \
   } while (0)
-#define EIGB_LAUNCH_CHECK() EIGB_CUDA_CHECK(cudaGetLastError())
+#define EIGB_LAUNCH_CHECK() do { ::eigb200::count_launch(1); EIGB_CUDA_CHECK(cudaGetLastError()); } while (0)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -98,6 +98,19 @@ Context& ctx();
 int ctx_init();
 // returns a device pointer to at least `bytes` of scratch (grown if needed; contents undefined)
 void* ctx_scratch(size_t bytes);
+
+// ---- optional stage profiling (CUDA events on the launching stream) and launch counting ------------------
+// Categories: 0 potrf, 1 hegst, 2 hetrd_panel (persistent panel kernel), 3 hetrd_her2k, 4 stedc, 5 ormtr,
+// 6 trsm, 7 other.
+enum ProfCat { PROF_POTRF = 0, PROF_HEGST, PROF_PANEL, PROF_HER2K, PROF_STEDC, PROF_ORMTR, PROF_TRSM, PROF_OTHER, PROF_NCAT };
+void prof_begin(int cat, cudaStream_t s);
+void prof_end(int cat, cudaStream_t s);
+void count_launch(int n = 1);
+struct ProfScope {
+  int cat; cudaStream_t s;
+  ProfScope(int c, cudaStream_t st) : cat(c), s(st) { prof_begin(cat, s); }
+  ~ProfScope() { prof_end(cat, s); }
+};
 
 // simple bump allocator over the context scratch
 struct Arena {

@@ -73,7 +73,55 @@ void* ctx_scratch(size_t bytes) {
 }  // namespace eigb200
 
 #include "stages.cuh"
+#include <vector>
 namespace eigb200 {
+
+// ---- profiling / launch counting ------------------------------------------------------------------------
+static bool g_prof_on = false;
+static long long g_launches = 0;
+struct ProfPair { cudaEvent_t a, b; int cat; };
+static std::vector<ProfPair> g_pairs;
+static std::vector<cudaEvent_t> g_pool;
+static cudaEvent_t g_open[PROF_NCAT];
+static double g_ms[PROF_NCAT];
+static int g_cnt[PROF_NCAT];
+
+void count_launch(int n) { g_launches += n; }
+static cudaEvent_t prof_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int cat, cudaStream_t s) {
+  if (!g_prof_on) return;
+  g_open[cat] = prof_event();
+  cudaEventRecord(g_open[cat], s);
+}
+void prof_end(int cat, cudaStream_t s) {
+  if (!g_prof_on) return;
+  cudaEvent_t b = prof_event();
+  cudaEventRecord(b, s);
+  g_pairs.push_back({g_open[cat], b, cat});
+}
+void prof_enable(int on) { g_prof_on = on != 0; }
+void prof_reset() {
+  for (auto& p : g_pairs) { g_pool.push_back(p.a); g_pool.push_back(p.b); }
+  g_pairs.clear();
+  for (int i = 0; i < PROF_NCAT; ++i) { g_ms[i] = 0; g_cnt[i] = 0; }
+  g_launches = 0;
+}
+// resolves all recorded pairs (synchronises the device) and returns accumulated ms / count per category
+void prof_collect(double* ms, int* cnt, long long* launches) {
+  cudaDeviceSynchronize();
+  for (auto& p : g_pairs) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) { g_ms[p.cat] += t; g_cnt[p.cat] += 1; }
+    g_pool.push_back(p.a); g_pool.push_back(p.b);
+  }
+  g_pairs.clear();
+  for (int i = 0; i < PROF_NCAT; ++i) { ms[i] = g_ms[i]; cnt[i] = g_cnt[i]; }
+  *launches = g_launches;
+}
+
 Options& opts() { static Options o; return o; }
 int set_option(const char* name, int value) {
   Options& o = opts();

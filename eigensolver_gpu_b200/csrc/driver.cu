@@ -97,14 +97,20 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
   cudaStream_t s = ctx().stream;
   const int m = iu - il + 1;
   int pinfo = 0;
-  if (potrf_upper<T>(s, n, B, ldb, &pinfo) != 0 || pinfo != 0) {
+  prof_begin(PROF_POTRF, s);
+  int prc = potrf_upper<T>(s, n, B, ldb, &pinfo);
+  prof_end(PROF_POTRF, s);
+  if (prc != 0 || pinfo != 0) {
     printf(" %s error: potrf failed!\n", name);
     if (pinfo != 0) set_last_error("%s error: potrf failed (B not positive definite at pivot %d)", name, pinfo);
     *info = -1;
     return -1;
   }
   // tril(A) -> Z, A <- U^-H A U^-1 (zhegvdx_gpu.F90:145-158)
-  if (hegst_upper<T>(s, n, A, lda, B, ldb, Z, ldz) != 0) { *info = -1; return -1; }
+  prof_begin(PROF_HEGST, s);
+  int hrc = hegst_upper<T>(s, n, A, lda, B, ldb, Z, ldz);
+  prof_end(PROF_HEGST, s);
+  if (hrc != 0) { *info = -1; return -1; }
   double* d_e = cplx ? rwork : reinterpret_cast<double*>(work);
   T* d_tau = cplx ? work : work + n;
   // the strict lower triangle of A is restored from Z before Z is overwritten (zheevd_gpu.F90:89-96); Z is
@@ -115,7 +121,10 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
     return -1;
   }
   // eigenvectors of the generalized problem: Z <- U^-1 Z (zhegvdx_gpu.F90:169)
-  if (trsm_upper<T>(s, 'L', 'N', n, m, B, ldb, Z, ldz) != 0) { *info = -1; return -1; }
+  prof_begin(PROF_TRSM, s);
+  int trc = trsm_upper<T>(s, 'L', 'N', n, m, B, ldb, Z, ldz);
+  prof_end(PROF_TRSM, s);
+  if (trc != 0) { *info = -1; return -1; }
   if (copy_results_to_host<T>(s, n, m, Z, ldz, w, Z_h, ldz_h, w_h, skip_host_copy != 0) != 0) {
     printf(" %s error: copy to host failed!\n", name);
     *info = -1;

@@ -90,6 +90,7 @@ int ormtr_upper(cudaStream_t s, int n, int m, const T* A, int64_t lda, const T* 
   const int nref = n - 1;
   const int nblk = (nref + ib - 1) / ib;
   if (scratch_bytes < ormtr_scratch_bytes(n, m, sizeof(T))) { set_last_error("ormtr: scratch too small"); return -1; }
+  ProfScope ps(PROF_ORMTR, s);
   Arena ar(scratch, scratch_bytes);
   const int64_t ldv = n;
   T* VW = ar.take<T>((size_t)n * n);

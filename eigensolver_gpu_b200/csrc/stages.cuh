@@ -4,6 +4,9 @@
 
 namespace eigb200 {
 
+void prof_enable(int on);
+void prof_reset();
+void prof_collect(double* ms, int* cnt, long long* launches);
 int set_option(const char* name, int value);
 int get_option(const char* name);
 

@@ -478,7 +478,9 @@ int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t
   w.gp = ar.take<GemmParams<double>>(2 * (size_t)(n / 2 + 2));
   if (!w.gp) { set_last_error("stedc: scratch arena exhausted"); return -1; }
 
+  ProfScope ps(PROF_STEDC, s);
   dc_scale_kernel<<<1, 1024, 0, s>>>(w);
+  count_launch(1);
   dc_leaf_kernel<<<cdiv(w.L, 4), 128, 0, s>>>(w);
   EIGB_LAUNCH_CHECK();
   static bool attr_set = false;
@@ -501,6 +503,7 @@ int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t
     dc_rank_kernel<<<gthr, 256, 0, s>>>(w, level);
     dc_zhat_kernel<<<gwarp, 256, 0, s>>>(w, level);
     dc_formu_kernel<<<gwarp, 256, 0, s>>>(w, level);
+    count_launch(7);
     EIGB_LAUNCH_CHECK();
     GemmParams<double> dummy{};
     if (gemm_launch<double>(s, false, true, dummy, w.gp, 2 * nmerge, maxn, maxn) != 0) return -1;

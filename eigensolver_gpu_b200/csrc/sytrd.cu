@@ -567,20 +567,25 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     // keep panels aligned so that the last (leftmost) panel absorbs the remainder
     if (hi > nb && (hi % nb) != 0) nbp = hi % nb;
     p.i0 = hi - nbp; p.nbp = nbp;
+    prof_begin(PROF_PANEL, s);
     if (coop) {
       EIGB_CUDA_CHECK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), s));
       void* args[] = {&p};
       EIGB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)panel_coop_kernel<T>, dim3(grid), dim3(NT), args, 0, s));
+      count_launch(1);
     } else {
       for (int cc = nbp - 1; cc >= -1; --cc) {
         phase_a_kernel<T><<<grid, NT, 0, s>>>(p, cc);
         if (cc < 0) break;
         phase_b_kernel<T><<<grid, NT, 0, s>>>(p, cc);
       }
-      EIGB_LAUNCH_CHECK();
+      count_launch(2 * nbp + 1);
+      EIGB_CUDA_CHECK(cudaGetLastError());
     }
+    prof_end(PROF_PANEL, s);
     // trailing update A(0:i0, 0:i0) -= V W^H + W V^H   (zhetrd_gpu.F90:67 / dsytrd_gpu.F90:66)
     if (p.i0 > 0) {
+      ProfScope ps(PROF_HER2K, s);
       if (her2k_upper<T>(s, 'N', p.i0, nbp, -1.0, A + (int64_t)p.i0 * lda, lda, p.W, p.ldw, 1.0, A, lda) != 0)
         return -1;
     }

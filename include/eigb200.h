@@ -34,6 +34,13 @@ int64_t eigb200_scratch_bytes(int n, int is_complex);
 int eigb200_set_option(const char* name, int value);
 int eigb200_get_option(const char* name);
 
+/* optional profiling: CUDA-event timing per stage category and a count of the kernels this library launched.
+ * categories (index into ms[8], cnt[8]): 0 potrf, 1 hegst, 2 hetrd panel kernel, 3 hetrd rank-2k update,
+ * 4 stedc, 5 back-transformation, 6 final trsm, 7 other.  collect() synchronises the device. */
+int eigb200_prof_enable(int on);
+int eigb200_prof_reset(void);
+int eigb200_prof_collect(double* ms, int* cnt, long long* launches);
+
 /* ---- generalized drivers (the drop-in entry points) ------------------------------------------------ */
 /* dsygvdx_gpu(N,A,lda,B,ldb,Z,ldz,il,iu,w,work,lwork,work_h,lwork_h,iwork_h,liwork_h,Z_h,ldz_h,w_h,info,
  *             _skip_host_copy)                                       dsygvdx_gpu.F90:71-72 */
