@@ -23,6 +23,7 @@ SIGNATURES = {
     "eigb200_prof_enable": (_i, [_i]),
     "eigb200_prof_reset": (_i, []),
     "eigb200_prof_collect": (_i, [_p, _p, _p]),
+    "eigb200_trace_read": (C.c_longlong, [_p, C.c_longlong]),
     "eigb200_set_option": (_i, [C.c_char_p, _i]),
     "eigb200_get_option": (_i, [C.c_char_p]),
     "eigb200_dsygvdx": (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _ip, _i]),

@@ -29,6 +29,13 @@ int eigb200_prof_enable(int on) { prof_enable(on); return 0; }
 int eigb200_prof_reset(void) { prof_reset(); return 0; }
 int eigb200_prof_collect(double* ms, int* cnt, long long* launches) { prof_collect(ms, cnt, launches); return 0; }
 
+long long eigb200_trace_read(unsigned long long* out, long long max_count) {
+  auto& v = trace_store();
+  long long n = (long long)v.size() < max_count ? (long long)v.size() : max_count;
+  for (long long i = 0; i < n; ++i) out[i] = v[i];
+  return n;
+}
+
 int eigb200_set_option(const char* name, int value) { return set_option(name, value); }
 int eigb200_get_option(const char* name) { return get_option(name); }
 

@@ -129,6 +129,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "bt_nb")) { if (value < 1 || value > 256) return -1; o.bt_nb = value; return 0; }
   if (!strcmp(name, "symv_tma")) { o.symv_tma = value; return 0; }
   if (!strcmp(name, "trd_coop")) { o.trd_coop = value; return 0; }
+  if (!strcmp(name, "trd_trace")) { o.trd_trace = value; return 0; }
   if (!strcmp(name, "verbose")) { ctx().verbose = value; return 0; }
   return -1;
 }

@@ -15,8 +15,13 @@ struct Options {
   int bt_nb = 128;      // back-transformation block (reference: 64, zheevd_gpu.F90:64)
   int symv_tma = 1;     // stage symv/hemv tiles through TMA (cp.async.bulk.tensor) when alignment allows
   int trd_coop = 1;     // persistent cooperative panel kernel (0: one launch per phase)
+  int trd_trace = 0;    // record per-column globaltimer stamps of the panel kernel (profiling aid)
 };
 Options& opts();
+}
+#include <vector>
+namespace eigb200 {
+std::vector<unsigned long long>& trace_store();
 
 // y = A x (A Hermitian, upper triangle read), deterministic tile reduction
 template <typename T> int hemv_upper(cudaStream_t s, int n, const T* A, int64_t lda, const T* x, T* y);

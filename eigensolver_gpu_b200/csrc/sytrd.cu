@@ -5,31 +5,53 @@
 // dsymv_gpu.F90:33-150) and the final-block kernel zhetd2_gpu/dsytd2_gpu.
 //
 // Design (B200-first, not the reference's 4 launches per column with FP64 atomics):
-//  * one persistent cooperative kernel per panel, 2 grid barriers per column:
+//  * one persistent cooperative kernel per panel (1 CTA of 512 threads per SM), 2 grid barriers per column:
 //      phase A (row-parallel "vector" phase): finish W(:,c+1) from the previous column's partial sums,
 //              bring column c up to date with the panel's reflectors, partial norms;
 //      phase B (tile phase): every CTA derives the Householder scalars (larfg) redundantly, then streams its
-//              share of the 64x64 tiles of the upper triangle ONCE, using each tile for A_IJ x_J and
-//              A_IJ^H x_I (warp-shuffle reductions), plus the V^H v / W^H v partial dots and v^H A v.
-//  * all cross-CTA reductions go through per-tile partial buffers summed in a fixed order: deterministic,
-//    no FP64 atomics (the reference's results depend on atomicAdd ordering).
+//              share of the 64x64 tiles of the upper triangle ONCE through a shared-memory ring filled by
+//              cp.async.bulk (TMA, SASS UBLKCP) and uses each tile for A_IJ x_J and A_IJ^H x_I; tiles are
+//              walked in column strips so that the transposed sums stay in registers for a whole strip and
+//              only one CTA barrier per tile is needed.  The V^H v / W^H v partial dots and v^H A v ride along.
+//  * all cross-CTA reductions go through partial buffers summed in a fixed order: deterministic, no FP64
+//    atomics (the reference's results depend on atomicAdd ordering).
 //  * w^H v is obtained algebraically (v^H A v - 2 Re(z1^H z2)), which removes a third barrier per column.
 //  * the same panel code runs down to column 1, so no separate unblocked 32x32 kernel is needed.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "stages.cuh"
-#include <cooperative_groups.h>
+#include "tmap.cuh"
+#include <vector>
+#include <string.h>
 
 namespace eigb200 {
+
+std::vector<unsigned long long>& trace_store() { static std::vector<unsigned long long> v; return v; }
 
 namespace {
 
 constexpr int TB = 64;        // symv/hemv tile edge
-constexpr int NT = 256;       // threads per CTA
-constexpr int NW = NT / 32;   // warps
-constexpr int CPW = TB / NW;  // tile columns per warp (8)
+constexpr int NT = 512;       // consumer/worker threads per CTA (16 warps: 4 tile rows each)
+constexpr int NW = NT / 32;
+constexpr int NTT = NT + 32;  // + one TMA producer warp
+constexpr int NWT = NTT / 32;
 constexpr int NBMAX = 128;    // max panel width
 constexpr int MAXZU = 64;     // max number of row chunks for the V^H v / W^H v partial dots
+constexpr int ZROWS = 512;    // rows per chunk of those dots (doubled while more than MAXZU chunks)
+constexpr int AW = 8;         // warps that split the per-row work in phase A
+
+// Ring of tile stages filled by cp.async.bulk (TMA).  One stage = a 64x64 tile stored with a padded column
+// stride (conflict-free 128-bit reads when a warp walks 32 columns) + the x slices of the tile's rows and columns.
+// A tile arrives as NBOX boxes of 16 doubles x 64 columns (8 KB each, one cp.async.bulk.tensor.2d per box) in the
+// 128-byte swizzled layout, which makes the "one lane per tile column" reads bank-conflict free.
+template <typename T> struct RingCfg;
+template <> struct RingCfg<double>  { static constexpr int STAGES = 6, NBOX = 4, DPE = 1; };
+template <> struct RingCfg<double2> { static constexpr int STAGES = 3, NBOX = 8, DPE = 2; };
+constexpr int BOX_BYTES = 128 * TB;
+template <typename T> __host__ __device__ constexpr int stage_elems() { return TB * TB + 2 * TB; }
+template <typename T> __host__ __device__ constexpr int ring_bytes() {
+  return RingCfg<T>::STAGES * stage_elems<T>() * (int)sizeof(T) + 1024;    // + slack for 1024-byte alignment
+}
 
 template <typename T>
 struct TrdP {
@@ -38,7 +60,7 @@ struct TrdP {
   T* W; int64_t ldw;           // W(:, c) <-> global column i0 + c
   double* d; double* e; T* tau;
   T* xbuf;                     // unscaled updated column
-  T* Pd; T* Pt; int64_t ldp;   // hemv partials: Pd[J*ldp + r] (direct), Pt[I*ldp + r] (transposed)
+  T* Pd; T* Pt; int64_t ldp;   // partials: Pd[J*ldp + r] (direct, from tile (I(r),J), J > I), Pt[k*ldp + r] (band k)
   T* zpart;                    // [MAXZU][2][NBMAX]
   double* npart;               // [G] partial sums of squares
   double* vavpart;             // [G] partial v^H A v
@@ -46,20 +68,64 @@ struct TrdP {
   unsigned* barrier;
   int* status;
   int vec_ok;                  // 16-byte loads allowed (real: A 16B aligned and lda even)
+  int use_tma;                 // off-diagonal tiles staged through the TMA ring (needs vec_ok)
+  unsigned long long* trace;   // optional: 5 globaltimer stamps per column (CTA 0), profiling aid
+};
+
+// per-thread pipeline state of the tile ring; persists across columns inside the cooperative kernel.
+// Consumers: par bit s = parity to wait for on full[s] (starts 0).  Producer: par bit s = parity to wait for on
+// empty[s] (starts 1: a fresh barrier counts as "previous phase complete").
+struct RingState {
+  int stage;
+  unsigned par;
 };
 
 template <typename T>
-struct PanelSmem {
+struct EngineSmem {
+  T yt[NW][TB];        // strip end: transposed partial sums of the 16 row-group warps
+  T ydiag[TB];         // D units: product of the diagonal tile with x_J (both triangles)
+};
+template <typename T>
+struct PhaseASmem {
   T z1[NBMAX], z2[NBMAX], rowV[NBMAX], rowW[NBMAX];
-  T red[NW * TB];
-  T yt[TB];
-  T xI[TB], xJ[TB];
-  T scal[4];        // generic scalar broadcast slots
-  double dscal[8];
+  T ared[AW * 32 * 3];   // per-warp slices of (t1, t2, wraw) for one group of 32 rows
+};
+// phase A and the tile engine never run at the same time: their scratch is overlaid
+template <typename T>
+struct PanelSmem {
+  union U {
+    PhaseASmem<T> a;
+    EngineSmem<T> e;
+    __device__ U() {}
+  } u;
+  T tred[NWT];
+  double dscal[NWT];
+  uint64_t full[8], empty[8];   // ring mbarriers
 };
 
 __device__ __forceinline__ double ldcg_(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ double2 ldcg_(const double2* p) { return __ldcg(p); }
+
+// ---- mbarrier / bulk-copy (TMA) wrappers ---------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok = 0;
+  const unsigned a = smem_u32(bar);
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // ---- grid barrier (monotonic counter, watchdog-protected) --------------------------------------------
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int* status) {
@@ -73,7 +139,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(bar) : "memory");
       if (v >= target) break;
       if (++spins > (1ull << 26)) { atomicExch(status, 77); break; }   // watchdog: never hang the GPU
-      __nanosleep(20);
     }
     __threadfence();
   }
@@ -87,15 +152,24 @@ __device__ __forceinline__ T block_sum(T v, T* red /* >= NW entries */) {
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   T s = zero_<T>();
-#pragma unroll
-  for (int w = 0; w < NW; ++w) s = add_(s, red[w]);
+  const int nw = blockDim.x >> 5;
+  for (int w = 0; w < nw; ++w) s = add_(s, red[w]);
   return s;
 }
 
 __host__ __device__ __forceinline__ int zchunk_rows(int n) {
-  int ch = 128;
+  int ch = ZROWS;
   while ((n + ch - 1) / ch > MAXZU) ch *= 2;
   return ch;
+}
+
+// tiles per strip chunk for an order-n product on G CTAs: aim at >= 6 units per CTA, at most 8 tiles per unit
+__host__ __device__ __forceinline__ int strip_len(int n, int G) {
+  const int Tn = (n + TB - 1) / TB;
+  int c = (Tn * (Tn - 1) / 2) / (6 * G);
+  if (c < 1) c = 1;
+  if (c > 8) c = 8;
+  return c;
 }
 
 // ---- Householder scalars: LAPACK ?larfg without the safmin loop (zhetrd_gpu.F90:277-331, dsytrd_gpu.F90:408-443)
@@ -126,169 +200,271 @@ __device__ __forceinline__ void larfg_scalars(double2 alpha, double xnorm2, doub
 }
 
 // =====================================================================================================
-// Tile engine: one 64x64 tile (I,J), I<=J, of the upper triangle of the leading n x n block of A.
-// Outputs: direct partial  Pd[J*ldp + I*TB + r] = sum_c A(r,c) x(c)         (off-diagonal and diagonal)
-//          transposed      Pt[I*ldp + J*TB + c] = sum_r conj(A(r,c)) x(r)    (off-diagonal only)
-// Returns this thread's contribution to Re(x^H A x).
-// Thread mapping: warp w owns tile columns [8w, 8w+8); lane l owns rows {2l,2l+1} (real, one 128-bit load)
-// or {l, l+32} (complex, two 128-bit loads): every global load is a coalesced 128-bit access.
+// Tile engine.  y = A x for the upper-stored Hermitian leading n x n block, as partial sums:
+//   units:  F(k, J)  band k (tile rows [kC, kC+C)), tile column J >= (k+1)C : C off-diagonal tiles
+//           D(J)     tile column J: off-diagonal tiles of the partial band floor(J/C) + the diagonal tile
+//   outputs: Pd[J*ldp + r]  = (A_IJ x_J)(r)            for every off-diagonal tile (I, J), r in block I
+//            Pt[k*ldp + c]  = sum over the unit's tiles of (A_IJ^H x_I)(c)  (+ the full diagonal-tile product for
+//                             D units), c in block J, k = the unit's band
+//   so  y(r) = sum_{J > I(r)} Pd[J][r] + sum_{k <= floor(I(r)/C)} Pt[k][r].
+// Thread mapping (512 threads): warp w -> row group wr = w%4 (16 rows), column group wc = w/4 (16 columns);
+// a thread holds RH consecutive rows x CQ columns (real 2x4, complex 1x8), read from the ring with 128-bit
+// conflict-free shared-memory loads (or from global memory with 128-bit loads when the ring is off).
 // =====================================================================================================
-template <typename T>
-__device__ __forceinline__ void tile_rows(int lane, int& r0, int& r1) {
-  if (is_cplx<T>::value) { r0 = lane; r1 = lane + 32; } else { r0 = 2 * lane; r1 = 2 * lane + 1; }
-}
-
-template <typename T>
-__device__ __forceinline__ void load_tile_regs(const T* __restrict__ A, int64_t lda, int n, int I, int J, int vec_ok,
-                                               T (&a)[CPW][2]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int r0, r1; tile_rows<T>(lane, r0, r1);
-  const int gr0 = I * TB + r0, gr1 = I * TB + r1;
-#pragma unroll
-  for (int q = 0; q < CPW; ++q) {
-    const int gc = J * TB + warp * CPW + q;
-    const T* col = A + (int64_t)gc * lda;
-    if (gc < n) {
-      if constexpr (!is_cplx<T>::value) {
-        if (vec_ok && gr1 < n) {
-          double2 v = __ldg(reinterpret_cast<const double2*>(col + gr0));
-          a[q][0] = v.x; a[q][1] = v.y;
-        } else {
-          a[q][0] = (gr0 < n) ? __ldg(col + gr0) : 0.0;
-          a[q][1] = (gr1 < n) ? __ldg(col + gr1) : 0.0;
-        }
-      } else {
-        a[q][0] = (gr0 < n) ? __ldg(col + gr0) : zero_<T>();
-        a[q][1] = (gr1 < n) ? __ldg(col + gr1) : zero_<T>();
-      }
+struct TileIter {
+  int unit, G, NF, total, Tn, C;
+  int J, I1, cur, band;
+  bool has_diag, done;
+  __device__ __forceinline__ void load_unit() {
+    if (unit >= total) { done = true; return; }
+    if (unit < NF) {
+      int u = unit, k = 0;
+      while (true) { const int cnt = Tn - (k + 1) * C; if (u < cnt) break; u -= cnt; ++k; }
+      band = k; J = (k + 1) * C + u; cur = k * C; I1 = k * C + C; has_diag = false;
     } else {
-      a[q][0] = zero_<T>(); a[q][1] = zero_<T>();
+      J = unit - NF; band = J / C; cur = band * C; I1 = J; has_diag = true;
     }
   }
-}
+  __device__ __forceinline__ void init(int cta, int G_, int Tn_, int C_) {
+    G = G_; Tn = Tn_; C = C_; done = false;
+    NF = 0;
+    for (int k = 0; Tn - (k + 1) * C > 0; ++k) NF += Tn - (k + 1) * C;
+    total = NF + Tn;
+    unit = cta;
+    load_unit();
+  }
+  // returns false when exhausted; otherwise the next tile of this CTA
+  __device__ __forceinline__ bool next(int& I, int& Jo, bool& diag, bool& first, bool& last, int& bnd) {
+    if (done) return false;
+    Jo = J; bnd = band;
+    const int I0 = band * C;
+    if (cur < I1) { I = cur; diag = false; first = (cur == I0); ++cur; last = (cur == I1) && !has_diag; }
+    else { I = J; diag = true; first = (I0 == I1); last = true; has_diag = false; }
+    if (last) { unit += G; load_unit(); }
+    return true;
+  }
+};
 
-// xI/xJ (tile slices of x) must already be in shared memory.  All threads call; contains __syncthreads.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+               :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" :: "n"(NT) : "memory"); }
+
 template <typename T>
-__device__ __forceinline__ double tile_compute(const T (&a)[CPW][2], int n, int I, int J, const T* xI, const T* xJ,
-                                               T* red, T* yt, T* Pd, T* Pt, int64_t ldp) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int r0, r1; tile_rows<T>(lane, r0, r1);
-  const int rr[2] = {r0, r1};
-  T accd[2] = {zero_<T>(), zero_<T>()};
-  T acct[CPW];
-  const bool diag = (I == J);
-  const T xr[2] = {xI[r0], xI[r1]};
-#pragma unroll
-  for (int q = 0; q < CPW; ++q) {
-    acct[q] = zero_<T>();
-    const int c = warp * CPW + q;
-    const T xc = xJ[c];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (!diag) {
-        fma_(accd[h], a[q][h], xc);
-        fmac_(acct[q], a[q][h], xr[h]);
-      } else {
-        if (rr[h] < c) {
-          fma_(accd[h], a[q][h], xc);
-          fmac_(acct[q], a[q][h], xr[h]);
-        } else if (rr[h] == c) {
-          fma_(accd[h], from_real<T>(real_(a[q][h])), xc);   // Hermitian: diagonal is real
-        }
-      }
-    }
+__device__ void ring_init(T* ring, uint64_t* full, uint64_t* empty, RingState& rs) {
+  constexpr int S = RingCfg<T>::STAGES;
+  // zero the ring once (tile columns beyond the matrix edge are never copied; they must not hold NaN patterns)
+  double* rz = reinterpret_cast<double*>(ring);
+  for (int i = threadIdx.x; i < (int)((ring_bytes<T>() - 1024) / sizeof(double)); i += blockDim.x) rz[i] = 0.0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  // transposed partials: reduce over the 32 lanes (rows)
-#pragma unroll
-  for (int q = 0; q < CPW; ++q) {
-    T s = warp_sum(acct[q]);
-    if (lane == 0) yt[warp * CPW + q] = s;
-  }
-  // direct partials: reduce over the 8 warps (column groups)
-  red[warp * TB + r0] = accd[0];
-  red[warp * TB + r1] = accd[1];
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
+  rs.stage = 0;
+  rs.par = (threadIdx.x >= NT) ? 0xffffffffu : 0u;
+}
+
+// sum of 4 per-lane values over the 32 lanes of a warp with 6 shuffles per scalar: on return lane 8*h holds the
+// total of v[h] (h = 0..3) in v[0]
+__device__ __forceinline__ void warp_reduce4(double (&v)[4], int lane) {
+  {
+    const bool up = lane & 16;
+    const double s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];
+    const double r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+    v[0] = (up ? v[2] : v[0]) + r0;
+    v[1] = (up ? v[3] : v[1]) + r1;
+  }
+  {
+    const bool up = lane & 8;
+    const double s = up ? v[0] : v[1];
+    const double r = __shfl_xor_sync(0xffffffffu, s, 8);
+    v[0] = (up ? v[1] : v[0]) + r;
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 4);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ void warp_reduce4(double2 (&v)[4], int lane) {
+  double re[4] = {v[0].x, v[1].x, v[2].x, v[3].x}, im[4] = {v[0].y, v[1].y, v[2].y, v[3].y};
+  warp_reduce4(re, lane); warp_reduce4(im, lane);
+  v[0] = mkz(re[0], im[0]);
+}
+
+// XR: (global index r, raw x value) -> x(r) (must return 0 for r >= n); xsrc: x stored with at least
+// roundup64(n) readable entries.  Returns this thread's share of Re(x^H A x).  All NTT threads must call.
+//   consumer warp w (0..15) owns tile rows [4w, 4w+4); lane l owns tile columns l and l+32.
+template <typename T, class XR>
+__device__ double tile_engine(const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc, XR xfix, T* Pd,
+                              T* Pt, int64_t ldp, int cta, int G, int C, bool tma, int vec_ok, T* ring, uint64_t* full,
+                              uint64_t* empty, RingState& rs, EngineSmem<T>& es, const CUtensorMap* tmap) {
+  constexpr int S = RingCfg<T>::STAGES, NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Tn = (n + TB - 1) / TB;
   double vav = 0.0;
-  if (tid < TB) {
-    T s = zero_<T>();
-#pragma unroll
-    for (int w = 0; w < NW; ++w) s = add_(s, red[w * TB + tid]);
-    const int gr = I * TB + tid;
-    if (diag) {
-      s = add_(s, yt[tid]);
-      if (gr < n) {
-        Pd[(int64_t)J * ldp + gr] = s;
-        T t = zero_<T>(); fmac_(t, xI[tid], s);
-        vav = real_(t);
+  TileIter it;
+  it.init(cta, G, Tn, C);
+  int I, J, band; bool diag, first, last;
+
+  if (warp >= NW) {
+    // ===================== TMA producer warp =====================
+    if (tma) {
+      while (it.next(I, J, diag, first, last, band)) {
+        if (diag) continue;
+        const int st = rs.stage;
+        mbar_wait(&empty[st], (rs.par >> st) & 1u);
+        rs.par ^= (1u << st);
+        T* dst = ring + (size_t)st * stage_elems<T>();
+        if (lane == 0) mbar_expect_tx(&full[st], (unsigned)(stage_elems<T>() * sizeof(T)));
+        __syncwarp();
+        if (lane < NBOX)
+          tma_load_2d(reinterpret_cast<char*>(dst) + lane * BOX_BYTES, tmap, (I * TB) * DPE + lane * 16, J * TB, &full[st]);
+        else if (lane == NBOX) bulk_copy_g2s(dst + TB * TB, xsrc + I * TB, (unsigned)(TB * sizeof(T)), &full[st]);
+        else if (lane == NBOX + 1) bulk_copy_g2s(dst + TB * TB + TB, xsrc + J * TB, (unsigned)(TB * sizeof(T)), &full[st]);
+        rs.stage = (st + 1) % S;
       }
-    } else {
-      Pd[(int64_t)J * ldp + gr] = s;                 // off-diagonal tile: all 64 rows are < n
-      T t = zero_<T>(); fmac_(t, xI[tid], s);
-      vav = 2.0 * real_(t);
-      const int gc = J * TB + tid;
-      if (gc < n) Pt[(int64_t)I * ldp + gc] = yt[tid];
+    }
+  } else {
+    // ===================== consumer warps =====================
+    const int r4 = 4 * warp;
+    T acct[2] = {zero_<T>(), zero_<T>()};
+    while (it.next(I, J, diag, first, last, band)) {
+      if (first) { acct[0] = zero_<T>(); acct[1] = zero_<T>(); }
+      T a[4][2], xr[4], xc[2];
+      if (tma && !diag) {
+        const int st = rs.stage;
+        mbar_wait(&full[st], (rs.par >> st) & 1u);
+        rs.par ^= (1u << st);
+        rs.stage = (st + 1) % S;
+        const T* tile = ring + (size_t)st * stage_elems<T>();
+        // this warp's 4 rows live in box (4w*DPE)/16, 16-byte chunks k0.. of each 128-byte column line; the
+        // SWIZZLE_128B layout stores chunk k of line c at chunk position k ^ (c & 7)
+        const char* box = reinterpret_cast<const char*>(tile) + ((r4 * DPE) / 16) * BOX_BYTES;
+        const int k0 = ((r4 * DPE) % 16) / 2;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = lane + 32 * q;
+          const char* line = box + c * 128;
+          if constexpr (!is_cplx<T>::value) {
+            const double2 v0 = *reinterpret_cast<const double2*>(line + (((k0) ^ (c & 7)) << 4));
+            const double2 v1 = *reinterpret_cast<const double2*>(line + (((k0 + 1) ^ (c & 7)) << 4));
+            a[0][q] = v0.x; a[1][q] = v0.y; a[2][q] = v1.x; a[3][q] = v1.y;
+          } else {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) a[h][q] = *reinterpret_cast<const double2*>(line + (((k0 + h) ^ (c & 7)) << 4));
+          }
+          xc[q] = xfix(J * TB + c, tile[TB * TB + TB + c]);
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) xr[h] = xfix(I * TB + r4 + h, tile[TB * TB + r4 + h]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);          // this warp is done with the stage
+      } else {
+        // diagonal tile (or ring disabled): masked loads straight from global memory
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = lane + 32 * q, gc = J * TB + c;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int r = r4 + h, gr = I * TB + r;
+            const bool ok = gr < n && gc < n && (!diag || r <= c);
+            a[h][q] = ok ? __ldg(A + gr + (int64_t)gc * lda) : zero_<T>();
+            if (diag && r == c) a[h][q] = from_real<T>(real_(a[h][q]));    // Hermitian: real diagonal
+          }
+          xc[q] = xfix(gc, gc < n ? xsrc[gc] : zero_<T>());
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { const int gr = I * TB + r4 + h; xr[h] = xfix(gr, gr < n ? xsrc[gr] : zero_<T>()); }
+      }
+      // ---- products: direct (rows) and transposed (columns)
+      T accd[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        accd[h] = zero_<T>();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          fma_(accd[h], a[h][q], xc[q]);
+          if (!diag || (r4 + h) < (lane + 32 * q)) fmac_(acct[q], a[h][q], xr[h]);
+        }
+        // v^H A v: conj(x_r) (A x)_r; an off-diagonal tile also stands for its mirror image, and so does the
+        // strictly upper part of a diagonal tile
+        if (!diag) {
+          T t = zero_<T>(); fmac_(t, xr[h], accd[h]);
+          vav += 2.0 * real_(t);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            T u = zero_<T>(); fma_(u, a[h][q], xc[q]);
+            T t = zero_<T>(); fmac_(t, xr[h], u);
+            vav += ((r4 + h) < (lane + 32 * q) ? 2.0 : 1.0) * real_(t);
+          }
+        }
+      }
+      warp_reduce4(accd, lane);
+      if ((lane & 7) == 0) {
+        const int h = lane >> 3;
+        if (!diag) Pd[(int64_t)J * ldp + I * TB + r4 + h] = accd[0];     // off-diagonal tile: all 64 rows are < n
+        else es.ydiag[r4 + h] = accd[0];
+      }
+      if (last) {
+        // strip end: combine the transposed sums of the 16 warps (+ the diagonal tile's direct part) -> Pt[band]
+        es.yt[warp][lane] = acct[0];
+        es.yt[warp][lane + 32] = acct[1];
+        consumer_barrier();
+        if (tid < TB) {
+          T s = diag ? es.ydiag[tid] : zero_<T>();
+#pragma unroll
+          for (int w = 0; w < NW; ++w) s = add_(s, es.yt[w][tid]);
+          if (J * TB + tid < n) Pt[(int64_t)band * ldp + J * TB + tid] = s;
+        }
+        consumer_barrier();
+      }
     }
   }
   __syncthreads();
   return vav;
 }
 
-__device__ __forceinline__ void tile_from_index(int idx, int& I, int& J) {
-  // idx = J(J+1)/2 + I, 0 <= I <= J
-  int j = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
-  while ((j + 1) * (j + 2) / 2 <= idx) ++j;
-  while (j * (j + 1) / 2 > idx) --j;
-  J = j; I = idx - j * (j + 1) / 2;
-}
-
-// sum of the partials belonging to row r of an order-n product (T_n = ceil(n/TB) tiles per side)
+// sum of the partials belonging to row r of an order-n product computed with strip length C
 template <typename T>
-__device__ __forceinline__ T gather_partials(const T* Pd, const T* Pt, int64_t ldp, int n, int r) {
+__device__ __forceinline__ T gather_partials(const T* Pd, const T* Pt, int64_t ldp, int n, int C, int r) {
   const int Tn = (n + TB - 1) / TB, I = r / TB;
-  T s0 = zero_<T>(), s1 = zero_<T>(), s2 = zero_<T>(), s3 = zero_<T>();
-  int J = I;
-  for (; J + 3 < Tn; J += 4) {
-    T a = ldcg_(Pd + (int64_t)J * ldp + r), b = ldcg_(Pd + (int64_t)(J + 1) * ldp + r);
-    T c = ldcg_(Pd + (int64_t)(J + 2) * ldp + r), d = ldcg_(Pd + (int64_t)(J + 3) * ldp + r);
-    s0 = add_(s0, a); s1 = add_(s1, b); s2 = add_(s2, c); s3 = add_(s3, d);
-  }
-  for (; J < Tn; ++J) s0 = add_(s0, ldcg_(Pd + (int64_t)J * ldp + r));
-  int K = 0;
-  for (; K + 3 < I; K += 4) {
-    T a = ldcg_(Pt + (int64_t)K * ldp + r), b = ldcg_(Pt + (int64_t)(K + 1) * ldp + r);
-    T c = ldcg_(Pt + (int64_t)(K + 2) * ldp + r), d = ldcg_(Pt + (int64_t)(K + 3) * ldp + r);
-    s0 = add_(s0, a); s1 = add_(s1, b); s2 = add_(s2, c); s3 = add_(s3, d);
-  }
-  for (; K < I; ++K) s1 = add_(s1, ldcg_(Pt + (int64_t)K * ldp + r));
-  return add_(add_(s0, s1), add_(s2, s3));
+  T s0 = zero_<T>(), s1 = zero_<T>();
+  for (int J = I + 1; J < Tn; ++J) s0 = add_(s0, ldcg_(Pd + (int64_t)J * ldp + r));
+  for (int k = 0; k <= I / C; ++k) s1 = add_(s1, ldcg_(Pt + (int64_t)k * ldp + r));
+  return add_(s0, s1);
 }
 
-// ---- stand-alone symv/hemv (eigb200_dsymv / eigb200_zhemv) ----------------------------------------------
+// ---- stand-alone symv/hemv (eigb200_dsymv / eigb200_zhemv): the same engine + a gather kernel -------------
 template <typename T>
-__global__ void __launch_bounds__(NT, 2) hemv_tiles_kernel(const T* __restrict__ A, int64_t lda, int n,
-                                                           const T* __restrict__ x, T* Pd, T* Pt, int64_t ldp,
-                                                           int vec_ok) {
-  __shared__ T red[NW * TB];
-  __shared__ T yt[TB];
-  __shared__ T xI[TB], xJ[TB];
-  const int Tn = (n + TB - 1) / TB, ntile = Tn * (Tn + 1) / 2;
-  for (int idx = blockIdx.x; idx < ntile; idx += gridDim.x) {
-    int I, J; tile_from_index(idx, I, J);
-    T a[CPW][2];
-    load_tile_regs<T>(A, lda, n, I, J, vec_ok, a);
-    if (threadIdx.x < TB) {
-      int gi = I * TB + threadIdx.x, gj = J * TB + threadIdx.x;
-      xI[threadIdx.x] = gi < n ? x[gi] : zero_<T>();
-      xJ[threadIdx.x] = gj < n ? x[gj] : zero_<T>();
-    }
-    __syncthreads();
-    tile_compute<T>(a, n, I, J, xI, xJ, red, yt, Pd, Pt, ldp);
-  }
+__global__ void __launch_bounds__(NTT, 1) hemv_tiles_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                            const T* __restrict__ A, int64_t lda, int n,
+                                                            const T* __restrict__ xpad, T* Pd, T* Pt, int64_t ldp, int C,
+                                                            int tma, int vec_ok) {
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
+  __shared__ EngineSmem<T> es;
+  __shared__ __align__(8) uint64_t full[8], empty[8];
+  T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
+  RingState rs; rs.stage = 0; rs.par = (threadIdx.x >= NT) ? 0xffffffffu : 0u;
+  if (tma) ring_init<T>(ring, full, empty, rs);
+  auto xfix = [n](int r, T raw) -> T { return r < n ? raw : zero_<T>(); };
+  tile_engine<T>(A, lda, n, xpad, xfix, Pd, Pt, ldp, blockIdx.x, gridDim.x, C, tma != 0, vec_ok, ring, full, empty, rs, es,
+                 &tmap);
 }
 template <typename T>
-__global__ void hemv_reduce_kernel(const T* Pd, const T* Pt, int64_t ldp, int n, T* y) {
+__global__ void hemv_reduce_kernel(const T* Pd, const T* Pt, int64_t ldp, int n, int C, T* y) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n) y[r] = gather_partials<T>(Pd, Pt, ldp, n, r);
+  if (r < n) y[r] = gather_partials<T>(Pd, Pt, ldp, n, C, r);
+}
+template <typename T>
+__global__ void pad_copy_kernel(const T* x, int n, T* xpad, int npad) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < npad) xpad[r] = r < n ? x[r] : zero_<T>();
 }
 
 // =====================================================================================================
@@ -303,6 +479,7 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
   const int jp = j + 1;                         // order of the product done for column c+1
   const bool have_prev = (c + 1 <= nbp - 1) && (jp >= 1) && !(c == -1 && p.i0 == 0);
   const int cprev = c + 1;
+  const int Cp = strip_len(jp, G);              // strip length used by the previous phase B
   T tau_p = zero_<T>();
   double alpha_p = 0.0;
 
@@ -313,29 +490,30 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
     const int nf = nbp - 1 - cprev;             // finished columns cc in (cprev, nbp)
     for (int q = tid; q < 2 * nf; q += NT) {
       const int which = q / nf, cc = cprev + 1 + (q % nf);
-      T s0 = zero_<T>(), s1 = zero_<T>();
+      const T* zp = p.zpart + (int64_t)which * NBMAX + cc;
+      T s0 = zero_<T>(), s1 = zero_<T>(), s2 = zero_<T>(), s3 = zero_<T>();
       int u = 0;
-      for (; u + 1 < nzu; u += 2) {
-        T a = ldcg_(p.zpart + ((int64_t)u * 2 + which) * NBMAX + cc);
-        T b = ldcg_(p.zpart + ((int64_t)(u + 1) * 2 + which) * NBMAX + cc);
-        s0 = add_(s0, a); s1 = add_(s1, b);
+      for (; u + 3 < nzu; u += 4) {
+        T a = ldcg_(zp + (int64_t)u * 2 * NBMAX), b = ldcg_(zp + (int64_t)(u + 1) * 2 * NBMAX);
+        T cc2 = ldcg_(zp + (int64_t)(u + 2) * 2 * NBMAX), d = ldcg_(zp + (int64_t)(u + 3) * 2 * NBMAX);
+        s0 = add_(s0, a); s1 = add_(s1, b); s2 = add_(s2, cc2); s3 = add_(s3, d);
       }
-      if (u < nzu) s0 = add_(s0, ldcg_(p.zpart + ((int64_t)u * 2 + which) * NBMAX + cc));
-      (which ? sm.z2 : sm.z1)[cc] = add_(s0, s1);
+      for (; u < nzu; ++u) s0 = add_(s0, ldcg_(zp + (int64_t)u * 2 * NBMAX));
+      (which ? sm.u.a.z2 : sm.u.a.z1)[cc] = add_(add_(s0, s1), add_(s2, s3));
     }
     // row j of V and W (finished columns); rowW[cprev] is filled below
     for (int cc = cprev + 1 + tid; cc < nbp; cc += NT) {
-      sm.rowV[cc] = ldcg_(p.A + j + (int64_t)(p.i0 + cc) * p.lda);
-      sm.rowW[cc] = ldcg_(p.W + j + (int64_t)cc * p.ldw);
+      sm.u.a.rowV[cc] = ldcg_(p.A + j + (int64_t)(p.i0 + cc) * p.lda);
+      sm.u.a.rowW[cc] = ldcg_(p.W + j + (int64_t)cc * p.ldw);
     }
-    if (tid == 0) sm.rowV[cprev] = from_real<T>(1.0);   // unit element of v_{c+1} sits in row j
+    if (tid == 0) sm.u.a.rowV[cprev] = from_real<T>(1.0);   // unit element of v_{c+1} sits in row j
     double vv = 0.0;
     for (int g = tid; g < G; g += NT) vv += __ldcg(p.vavpart + g);
     vv = block_sum<double>(vv, sm.dscal);    // (contains __syncthreads: z1/z2/rowV/rowW visible after it)
     // rho = v^H A v - 2 Re(z1^H z2)
     double zz = 0.0;
     for (int cc = cprev + 1 + tid; cc < nbp; cc += NT) {
-      T t = zero_<T>(); fmac_(t, sm.z1[cc], sm.z2[cc]);
+      T t = zero_<T>(); fmac_(t, sm.u.a.z1[cc], sm.u.a.z2[cc]);
       zz += real_(t);
     }
     __syncthreads();
@@ -346,57 +524,86 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
     // row j of the new W column: u_j = wraw_j - sum_cc (W(j,cc) z1(cc) + V(j,cc) z2(cc))
     T part = zero_<T>();
     for (int cc = cprev + 1 + tid; cc < nbp; cc += NT) {
-      fma_(part, sm.rowW[cc], sm.z1[cc]);
-      fma_(part, sm.rowV[cc], sm.z2[cc]);
+      fma_(part, sm.u.a.rowW[cc], sm.u.a.z1[cc]);
+      fma_(part, sm.u.a.rowV[cc], sm.u.a.z2[cc]);
     }
     __syncthreads();
-    part = block_sum<T>(part, sm.red);
+    part = block_sum<T>(part, sm.tred);
     if (warp == 0) {
       // wraw_j: lane-strided gather of the partials of row j, fixed order
       const int Tn = (jp + TB - 1) / TB, I = j / TB;
       T wr = zero_<T>();
-      for (int J = I + lane; J < Tn; J += 32) wr = add_(wr, ldcg_(p.Pd + (int64_t)J * p.ldp + j));
-      for (int K = lane; K < I; K += 32) wr = add_(wr, ldcg_(p.Pt + (int64_t)K * p.ldp + j));
+      for (int J = I + 1 + lane; J < Tn; J += 32) wr = add_(wr, ldcg_(p.Pd + (int64_t)J * p.ldp + j));
+      for (int k = lane; k <= I / Cp; k += 32) wr = add_(wr, ldcg_(p.Pt + (int64_t)k * p.ldp + j));
       wr = warp_sum(wr);
       if (lane == 0) {
         T w = mul_(tau_p, sub_(wr, part));
-        sm.rowW[cprev] = add_(w, from_real<T>(alpha_p));    // + alpha' * v(j), v(j) = 1
+        sm.u.a.rowW[cprev] = add_(w, from_real<T>(alpha_p));    // + alpha' * v(j), v(j) = 1
       }
     }
     __syncthreads();
   }
 
-  // -- row-parallel part
+  // -- row-parallel part: groups of 32 consecutive rows are dealt to the CTAs; inside a CTA AW warps split the
+  //    panel columns and the partial-sum slots of those rows, warp 0 combines and finishes them
   double nrm = 0.0;
   const int nrows = (c >= 0) ? (j + 1) : jp;     // c == -1: only finish W(:, 0), rows [0, i0)
-  for (int r = cta * NT + tid; r < nrows; r += G * NT) {
-    T t1 = zero_<T>(), t2 = zero_<T>();
-    for (int cc = cprev + 1; cc < nbp; ++cc) {
-      const T vv = ldcg_(p.A + r + (int64_t)(p.i0 + cc) * p.lda);
-      const T ww = ldcg_(p.W + r + (int64_t)cc * p.ldw);
-      if (have_prev) { fma_(t1, ww, sm.z1[cc]); fma_(t1, vv, sm.z2[cc]); }
-      if (c >= 0) { fma_(t2, vv, conj_(sm.rowW[cc])); fma_(t2, ww, conj_(sm.rowV[cc])); }
+  const int ngroups = (nrows + 31) / 32;
+  const int Tn = (jp + TB - 1) / TB;
+  for (int g = cta; g < ngroups; g += G) {
+    const int r = g * 32 + lane;
+    const bool rv = r < nrows;
+    if (warp < AW) {
+      T t1 = zero_<T>(), t2 = zero_<T>(), wr = zero_<T>();
+      if (rv) {
+        for (int cc = cprev + 1 + warp; cc < nbp; cc += AW) {
+          const T vv = ldcg_(p.A + r + (int64_t)(p.i0 + cc) * p.lda);
+          const T ww = ldcg_(p.W + r + (int64_t)cc * p.ldw);
+          if (have_prev) { fma_(t1, ww, sm.u.a.z1[cc]); fma_(t1, vv, sm.u.a.z2[cc]); }
+          if (c >= 0) { fma_(t2, vv, conj_(sm.u.a.rowW[cc])); fma_(t2, ww, conj_(sm.u.a.rowV[cc])); }
+        }
+        if (have_prev) {
+          const int I = (g * 32) / TB;
+          const int nd = Tn - (I + 1);                // direct slots J = I+1 .. Tn-1
+          const int nt = I / Cp + 1;                  // band slots k = 0 .. I/Cp
+          for (int q = warp; q < nd + nt; q += AW) {
+            const T* src = (q < nd) ? (p.Pd + (int64_t)(I + 1 + q) * p.ldp) : (p.Pt + (int64_t)(q - nd) * p.ldp);
+            wr = add_(wr, ldcg_(src + r));
+          }
+        }
+      }
+      T* ar = sm.u.a.ared + (warp * 32 + lane) * 3;
+      ar[0] = t1; ar[1] = t2; ar[2] = wr;
     }
-    if (have_prev) {
-      const T wraw = gather_partials<T>(p.Pd, p.Pt, p.ldp, jp, r);
-      const T vnew = ldcg_(p.A + r + (int64_t)(j + 1) * p.lda);
-      T wnew = mul_(tau_p, sub_(wraw, t1));
-      wnew = add_(wnew, scale_(vnew, alpha_p));
-      p.W[r + (int64_t)cprev * p.ldw] = wnew;
-      if (c >= 0) { fma_(t2, vnew, conj_(sm.rowW[cprev])); fma_(t2, wnew, conj_(sm.rowV[cprev])); }
-    }
-    if (c >= 0) {
-      T a = sub_(ldcg_(p.A + r + (int64_t)j * p.lda), t2);
-      if (r == j) {
-        a = from_real<T>(real_(a));
-        p.d[j] = real_(a);
-        p.A[j + (int64_t)j * p.lda] = a;
-      } else {
-        p.xbuf[r] = a;
-        if (r < j - 1) nrm += abs2_(a);
-        if (r == j - 1) *p.alpha_slot = a;
+    __syncthreads();
+    if (warp == 0 && rv) {
+      T t1 = zero_<T>(), t2 = zero_<T>(), wr = zero_<T>();
+#pragma unroll
+      for (int w = 0; w < AW; ++w) {
+        const T* a2 = sm.u.a.ared + (w * 32 + lane) * 3;
+        t1 = add_(t1, a2[0]); t2 = add_(t2, a2[1]); wr = add_(wr, a2[2]);
+      }
+      if (have_prev) {
+        const T vnew = ldcg_(p.A + r + (int64_t)(j + 1) * p.lda);
+        T wnew = mul_(tau_p, sub_(wr, t1));
+        wnew = add_(wnew, scale_(vnew, alpha_p));
+        p.W[r + (int64_t)cprev * p.ldw] = wnew;
+        if (c >= 0) { fma_(t2, vnew, conj_(sm.u.a.rowW[cprev])); fma_(t2, wnew, conj_(sm.u.a.rowV[cprev])); }
+      }
+      if (c >= 0) {
+        T a = sub_(ldcg_(p.A + r + (int64_t)j * p.lda), t2);
+        if (r == j) {
+          a = from_real<T>(real_(a));
+          p.d[j] = real_(a);
+          p.A[j + (int64_t)j * p.lda] = a;
+        } else {
+          p.xbuf[r] = a;
+          if (r < j - 1) nrm += abs2_(a);
+          if (r == j - 1) *p.alpha_slot = a;
+        }
       }
     }
+    __syncthreads();
   }
   if (c >= 0) {
     __syncthreads();
@@ -406,7 +613,7 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
 }
 
 template <typename T>
-__device__ void phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
+__device__ void phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingState& rs, const CUtensorMap* tmap) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
   const int j = p.i0 + c;            // order of the product; reflector index j-1
@@ -420,110 +627,143 @@ __device__ void phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
   larfg_scalars(alpha, x2, beta, tau, scale);
   if (cta == 0 && tid == 0) { p.e[j - 1] = beta; p.tau[j - 1] = tau; }
   // -- store v in A(:, j) (nobody reads column j in this phase)
+  if (tid < NT)
   for (int r = cta * NT + tid; r < j; r += G * NT) {
     T v = (r == j - 1) ? from_real<T>(1.0) : mul_(scale, ldcg_(p.xbuf + r));
     p.A[r + (int64_t)j * p.lda] = v;
   }
-  auto xval = [&](int r) -> T {
+  auto xfix = [j, scale](int r, T raw) -> T {
     if (r >= j) return zero_<T>();
     if (r == j - 1) return from_real<T>(1.0);
-    return mul_(scale, ldcg_(p.xbuf + r));
+    return mul_(scale, raw);
   };
+  auto xval = [&](int r) -> T { return xfix(r, r < j ? p.xbuf[r] : zero_<T>()); };
+  // -- partial dots z1 = V^H v, z2 = W^H v: unit = (row chunk u, group of NW (which, cc) pairs), one pair per warp
   const int nf = p.nbp - 1 - c;      // finished columns cc in (c, nbp)
-  const int zch = zchunk_rows(j);
-  const int nzu = (nf > 0) ? (j + zch - 1) / zch : 0;
-  const int Tn = (j + TB - 1) / TB, ntile = Tn * (Tn + 1) / 2;
-  double vav = 0.0;
-  for (int unit = cta; unit < nzu + ntile; unit += G) {
-    if (unit < nzu) {
-      // ---- partial dots z1 = V^H v, z2 = W^H v over rows [unit*zch, ...)
-      const int rbeg = unit * zch, rend = min(j, rbeg + zch);
-      for (int q = warp; q < 2 * nf; q += NW) {
+  if (nf > 0 && warp < NW) {
+    const int zch = zchunk_rows(j);
+    const int nzch = (j + zch - 1) / zch;
+    const int ngrp = (2 * nf + NW - 1) / NW;
+    // start at the far end of the CTA range so that these units do not pile onto the CTAs with the longest strips
+    for (int unit = (G - 1 - cta); unit < nzch * ngrp; unit += G) {
+      const int u = unit / ngrp, grp = unit % ngrp;
+      const int q = grp * NW + warp;
+      if (q < 2 * nf) {
+        const int rbeg = u * zch, rend = min(j, rbeg + zch);
         const int which = q / nf, cc = c + 1 + (q % nf);
         const T* col = which ? (p.W + (int64_t)cc * p.ldw) : (p.A + (int64_t)(p.i0 + cc) * p.lda);
         T s = zero_<T>();
         for (int r = rbeg + lane; r < rend; r += 32) fmac_(s, ldcg_(col + r), xval(r));
         s = warp_sum(s);
-        if (lane == 0) p.zpart[((int64_t)unit * 2 + which) * NBMAX + cc] = s;
+        if (lane == 0) p.zpart[((int64_t)u * 2 + which) * NBMAX + cc] = s;
       }
-    } else {
-      int I, J; tile_from_index(unit - nzu, I, J);
-      T a[CPW][2];
-      load_tile_regs<T>(p.A, p.lda, j, I, J, p.vec_ok, a);
-      __syncthreads();
-      if (tid < TB) sm.xI[tid] = xval(I * TB + tid);
-      else if (tid < 2 * TB) sm.xJ[tid - TB] = xval(J * TB + tid - TB);
-      __syncthreads();
-      vav += tile_compute<T>(a, j, I, J, sm.xI, sm.xJ, sm.red, sm.yt, p.Pd, p.Pt, p.ldp);
     }
   }
-  __syncthreads();
+  // -- the tile engine: w_raw partials and v^H A v
+  __syncthreads();     // phase-A scratch is dead from here on: the engine overlays it
+  double vav = tile_engine<T>(p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, cta, G, strip_len(j, G), p.use_tma != 0,
+                              p.vec_ok, ring, sm.full, sm.empty, rs, sm.u.e, tmap);
   vav = block_sum<double>(vav, sm.dscal);
   if (tid == 0) p.vavpart[cta] = vav;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(NT, 2) panel_coop_kernel(TrdP<T> p) {
+__global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constant__ CUtensorMap tmap, TrdP<T> p) {
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ PanelSmem<T> sm;
+  T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
+  RingState rs; rs.stage = 0; rs.par = (threadIdx.x >= NT) ? 0xffffffffu : 0u;
+  if (p.use_tma) ring_init<T>(ring, sm.full, sm.empty, rs);
   unsigned target = 0;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  auto stamp = [&](int c, int k) {
+    if (tr) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.trace[(size_t)(p.i0 + c) * 5 + k] = t;
+    }
+  };
   for (int c = p.nbp - 1; c >= -1; --c) {
+    if (c >= 0) stamp(c, 0);
     phase_a<T>(p, c, sm);
     if (c < 0) break;
+    stamp(c, 1);
     target += gridDim.x;
     grid_barrier(p.barrier, target, p.status);
-    phase_b<T>(p, c, sm);
+    stamp(c, 2);
+    phase_b<T>(p, c, sm, ring, rs, &tmap);
+    stamp(c, 3);
     target += gridDim.x;
     grid_barrier(p.barrier, target, p.status);
+    stamp(c, 4);
   }
 }
 template <typename T>
-__global__ void __launch_bounds__(NT, 2) phase_a_kernel(TrdP<T> p, int c) {
+__global__ void __launch_bounds__(NTT, 1) phase_a_kernel(TrdP<T> p, int c) {
   __shared__ PanelSmem<T> sm;
   phase_a<T>(p, c, sm);
 }
 template <typename T>
-__global__ void __launch_bounds__(NT, 2) phase_b_kernel(TrdP<T> p, int c) {
+__global__ void __launch_bounds__(NTT, 1) phase_b_kernel(const __grid_constant__ CUtensorMap tmap, TrdP<T> p, int c) {
+  extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ PanelSmem<T> sm;
-  phase_b<T>(p, c, sm);
+  T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
+  RingState rs; rs.stage = 0; rs.par = (threadIdx.x >= NT) ? 0xffffffffu : 0u;
+  if (p.use_tma) ring_init<T>(ring, sm.full, sm.empty, rs);
+  phase_b<T>(p, c, sm, ring, rs, &tmap);
 }
 
 template <typename T>
-int panel_grid(int& grid) {
+int panel_grid(int& grid, size_t dyn_smem) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EIGB_CUDA_CHECK(cudaFuncSetAttribute(panel_coop_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
+    EIGB_CUDA_CHECK(cudaFuncSetAttribute(phase_b_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
+    EIGB_CUDA_CHECK(cudaFuncSetAttribute(hemv_tiles_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
+    attr_set = true;
+  }
   int per_sm = 0;
-  EIGB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_coop_kernel<T>, NT, 0));
+  EIGB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_coop_kernel<T>, NTT, dyn_smem));
   if (per_sm < 1) { set_last_error("panel kernel does not fit on an SM"); return -1; }
-  if (per_sm > 2) per_sm = 2;
-  grid = per_sm * ctx().num_sms;
+  grid = ctx().num_sms;      // one persistent CTA per SM
   return 0;
 }
 
-}  // namespace
-
 // scratch layout helper shared by hemv() and hetrd()
 template <typename T>
-static size_t partial_elems(int n, int64_t& ldp) {
+size_t partial_elems(int n, int64_t& ldp) {
   ldp = ((int64_t)n + 63) & ~int64_t(63);
   int Tn = (n + TB - 1) / TB;
   return (size_t)ldp * (size_t)(Tn > 0 ? Tn : 1);
 }
+
+}  // namespace
 
 template <typename T>
 int hemv_upper(cudaStream_t s, int n, const T* A, int64_t lda, const T* x, T* y) {
   if (n <= 0) return 0;
   int64_t ldp;
   size_t pe = partial_elems<T>(n, ldp);
-  void* scr = ctx_scratch(2 * pe * sizeof(T) + 512);
+  const int npad = ((n + 63) & ~63) + 64;
+  void* scr = ctx_scratch((2 * pe + npad) * sizeof(T) + 1024);
   if (!scr) return -1;
   Arena ar(scr, ctx().scratch_bytes);
   T* Pd = ar.take<T>(pe);
   T* Pt = ar.take<T>(pe);
-  int vec_ok = is_cplx<T>::value ? 1 : ((((uintptr_t)A & 15) == 0 && (lda & 1) == 0) ? 1 : 0);
-  int Tn = (n + TB - 1) / TB, ntile = Tn * (Tn + 1) / 2;
-  int grid = 2 * ctx().num_sms;
-  if (grid > ntile) grid = ntile;
-  hemv_tiles_kernel<T><<<grid, NT, 0, s>>>(A, lda, n, x, Pd, Pt, ldp, vec_ok);
+  T* xpad = ar.take<T>(npad);
+  const int vec_ok = is_cplx<T>::value ? 1 : ((((uintptr_t)A & 15) == 0 && (lda & 1) == 0) ? 1 : 0);
+  int tma = (opts().symv_tma != 0 && vec_ok && ((uintptr_t)A & 15) == 0) ? 1 : 0;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (tma && make_tmap_f64_box16x64(&tmap, A, (uint64_t)n * RingCfg<T>::DPE, (uint64_t)n, (uint64_t)lda * sizeof(T)) != 0)
+    tma = 0;
+  int grid = 0;
+  if (panel_grid<T>(grid, tma ? ring_bytes<T>() : 0) != 0) return -1;
+  const int C = strip_len(n, grid);
+  pad_copy_kernel<T><<<cdiv(npad, 256), 256, 0, s>>>(x, n, xpad, npad);
+  hemv_tiles_kernel<T><<<grid, NTT, tma ? ring_bytes<T>() : 0, s>>>(tmap, A, lda, n, xpad, Pd, Pt, ldp, C, tma, vec_ok);
   EIGB_LAUNCH_CHECK();
-  hemv_reduce_kernel<T><<<cdiv(n, 256), 256, 0, s>>>(Pd, Pt, ldp, n, y);
+  hemv_reduce_kernel<T><<<cdiv(n, 256), 256, 0, s>>>(Pd, Pt, ldp, n, C, y);
   EIGB_LAUNCH_CHECK();
   return 0;
 }
@@ -536,11 +776,18 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   if (n <= 0) return 0;
   Context& c = ctx();
   const int nb = opts().trd_nb < NBMAX ? opts().trd_nb : NBMAX;
+  const int vec_ok = is_cplx<T>::value ? 1 : ((((uintptr_t)A & 15) == 0 && (lda & 1) == 0) ? 1 : 0);
+  int use_tma = (opts().symv_tma != 0 && vec_ok && ((uintptr_t)A & 15) == 0) ? 1 : 0;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (use_tma && make_tmap_f64_box16x64(&tmap, A, (uint64_t)n * RingCfg<T>::DPE, (uint64_t)n, (uint64_t)lda * sizeof(T)) != 0)
+    use_tma = 0;
+  const size_t dyn = use_tma ? (size_t)ring_bytes<T>() : 0;
   int grid = 0;
-  if (panel_grid<T>(grid) != 0) return -1;
+  if (panel_grid<T>(grid, dyn) != 0) return -1;
   int64_t ldp;
   size_t pe = partial_elems<T>(n, ldp);
-  size_t bytes = (2 * pe + (size_t)n * nb + (size_t)n + (size_t)MAXZU * 2 * NBMAX + 64) * sizeof(T) +
+  size_t bytes = (2 * pe + (size_t)n * nb + (size_t)n + 256 + (size_t)MAXZU * 2 * NBMAX + 64) * sizeof(T) +
                  (size_t)(2 * grid + 64) * sizeof(double) + 4096 + 16 * 256;
   void* scr = ctx_scratch(bytes);
   if (!scr) return -1;
@@ -549,7 +796,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   p.A = A; p.lda = lda; p.d = d; p.e = e; p.tau = tau;
   p.Pd = ar.take<T>(pe); p.Pt = ar.take<T>(pe); p.ldp = ldp;
   p.W = ar.take<T>((size_t)n * nb); p.ldw = n;
-  p.xbuf = ar.take<T>(n);
+  p.xbuf = ar.take<T>((size_t)n + 128);
   p.zpart = ar.take<T>((size_t)MAXZU * 2 * NBMAX);
   p.alpha_slot = ar.take<T>(16);
   p.npart = ar.take<double>(grid);
@@ -557,27 +804,33 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   p.barrier = ar.take<unsigned>(64);
   p.status = c.d_info;
   if (!p.barrier) { set_last_error("hetrd: scratch arena too small"); return -1; }
-  p.vec_ok = is_cplx<T>::value ? 1 : ((((uintptr_t)A & 15) == 0 && (lda & 1) == 0) ? 1 : 0);
+  p.vec_ok = vec_ok;
+  p.use_tma = use_tma;
+  p.trace = nullptr;
+  if (opts().trd_trace) {
+    if (cudaMalloc(&p.trace, (size_t)n * 5 * sizeof(unsigned long long)) != cudaSuccess) p.trace = nullptr;
+    else cudaMemsetAsync(p.trace, 0, (size_t)n * 5 * sizeof(unsigned long long), s);
+  }
   EIGB_CUDA_CHECK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
   const bool coop = opts().trd_coop != 0;
 
   int hi = n;                         // columns [0, hi) still to reduce
   while (hi > 0) {
     int nbp = hi < nb ? hi : nb;
-    // keep panels aligned so that the last (leftmost) panel absorbs the remainder
+    // the first (rightmost) panel absorbs the remainder so that the others are aligned to nb
     if (hi > nb && (hi % nb) != 0) nbp = hi % nb;
     p.i0 = hi - nbp; p.nbp = nbp;
     prof_begin(PROF_PANEL, s);
     if (coop) {
       EIGB_CUDA_CHECK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), s));
-      void* args[] = {&p};
-      EIGB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)panel_coop_kernel<T>, dim3(grid), dim3(NT), args, 0, s));
+      void* args[] = {&tmap, &p};
+      EIGB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)panel_coop_kernel<T>, dim3(grid), dim3(NTT), args, dyn, s));
       count_launch(1);
     } else {
       for (int cc = nbp - 1; cc >= -1; --cc) {
-        phase_a_kernel<T><<<grid, NT, 0, s>>>(p, cc);
+        phase_a_kernel<T><<<grid, NTT, 0, s>>>(p, cc);
         if (cc < 0) break;
-        phase_b_kernel<T><<<grid, NT, 0, s>>>(p, cc);
+        phase_b_kernel<T><<<grid, NTT, dyn, s>>>(tmap, p, cc);
       }
       count_launch(2 * nbp + 1);
       EIGB_CUDA_CHECK(cudaGetLastError());
@@ -594,6 +847,11 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   int st = 0;
   EIGB_CUDA_CHECK(cudaMemcpyAsync(&st, p.status, sizeof(int), cudaMemcpyDeviceToHost, s));
   EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (p.trace) {
+    trace_store().resize((size_t)n * 5);
+    cudaMemcpy(trace_store().data(), p.trace, (size_t)n * 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+  }
   if (st != 0) { set_last_error("hetrd: device status %d (grid barrier watchdog)", st); return -1; }
   return 0;
 }

@@ -223,6 +223,70 @@ int restore_lower(cudaStream_t s, int n, T* A, int64_t lda, const T* save, int64
   return 0;
 }
 
+// ---- recursive building blocks --------------------------------------------------------------------------
+// Splitting [lo, hi) at a multiple of 64 near the middle turns almost all flops into GEMMs with a large inner
+// dimension (half of them at K = n/2, a quarter at K = n/4, ...), which is where the DMMA kernel is efficient;
+// only the 64-wide leaves use the inverted diagonal blocks.
+static inline int split_point(int lo, int hi) {
+  const int nb = (hi - lo + NB - 1) / NB;
+  return lo + (nb / 2) * NB;
+}
+
+// Triangular solve restricted to the diagonal range [lo, hi) of U.  B is addressed with GLOBAL indices:
+//   side 'L': rows [lo, hi) of B, `other` columns;   side 'R': columns [lo, hi) of B, `other` rows.
+// Dinv[b] must hold the inverse of the b-th 64x64 diagonal block of U for every block in the range.
+template <typename T>
+int trsm_rec(cudaStream_t s, char side, char trans, int lo, int hi, int other, const T* U, int64_t ldu, T* B,
+             int64_t ldb, const T* Dinv) {
+  if (hi - lo <= NB) {
+    const T* M = Dinv + (int64_t)(lo / NB) * NB * NB;
+    const int nb = hi - lo;
+    if (side == 'L' && trans == 'N')
+      diag_mult_kernel<T, true, false><<<cdiv(other, NB), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+    else if (side == 'L')
+      diag_mult_kernel<T, true, true><<<cdiv(other, NB), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+    else
+      diag_mult_kernel<T, false, false><<<cdiv(other, NB), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+    EIGB_LAUNCH_CHECK();
+    return 0;
+  }
+  const int mid = split_point(lo, hi);
+  const int n1 = mid - lo, n2 = hi - mid;
+  const T* U12 = U + lo + (int64_t)mid * ldu;          // n1 x n2
+  if (side == 'L' && trans == 'N') {                   // X2 = U22^-1 B2 ; B1 -= U12 X2 ; X1 = U11^-1 B1
+    if (trsm_rec<T>(s, side, trans, mid, hi, other, U, ldu, B, ldb, Dinv) != 0) return -1;
+    if (gemm<T>(s, 'N', 'N', n1, other, n2, -1.0, U12, ldu, B + mid, ldb, 1.0, B + lo, ldb) != 0) return -1;
+    return trsm_rec<T>(s, side, trans, lo, mid, other, U, ldu, B, ldb, Dinv);
+  } else if (side == 'L') {                            // X1 = U11^-H B1 ; B2 -= U12^H X1 ; X2 = U22^-H B2
+    if (trsm_rec<T>(s, side, trans, lo, mid, other, U, ldu, B, ldb, Dinv) != 0) return -1;
+    if (gemm<T>(s, 'C', 'N', n2, other, n1, -1.0, U12, ldu, B + lo, ldb, 1.0, B + mid, ldb) != 0) return -1;
+    return trsm_rec<T>(s, side, trans, mid, hi, other, U, ldu, B, ldb, Dinv);
+  } else {                                             // X1 = B1 U11^-1 ; B2 -= X1 U12 ; X2 = B2 U22^-1
+    if (trsm_rec<T>(s, side, trans, lo, mid, other, U, ldu, B, ldb, Dinv) != 0) return -1;
+    if (gemm<T>(s, 'N', 'N', other, n2, n1, -1.0, B + (int64_t)lo * ldb, ldb, U12, ldu, 1.0, B + (int64_t)mid * ldb, ldb)
+        != 0) return -1;
+    return trsm_rec<T>(s, side, trans, mid, hi, other, U, ldu, B, ldb, Dinv);
+  }
+}
+
+template <typename T>
+int potrf_rec(cudaStream_t s, int lo, int hi, T* A, int64_t lda, T* Dinv, int* dinfo) {
+  if (hi - lo <= NB) {
+    potf2_block_kernel<T><<<1, 256, blk_smem<T>(), s>>>(A, lda, lo, hi - lo, Dinv + (int64_t)(lo / NB) * NB * NB, dinfo);
+    EIGB_LAUNCH_CHECK();
+    return 0;
+  }
+  const int mid = split_point(lo, hi);
+  if (potrf_rec<T>(s, lo, mid, A, lda, Dinv, dinfo) != 0) return -1;
+  // U12 = U11^-H A12 : rows [lo, mid) of the column block [mid, hi)
+  T* A12cols = A + (int64_t)mid * lda;
+  if (trsm_rec<T>(s, 'L', 'C', lo, mid, hi - mid, A, lda, A12cols, lda, Dinv) != 0) return -1;
+  // A22 -= U12^H U12 (upper)
+  if (herk_upper<T>(s, 'C', hi - mid, mid - lo, -1.0, A + lo + (int64_t)mid * lda, lda, 1.0,
+                    A + mid + (int64_t)mid * lda, lda) != 0) return -1;
+  return potrf_rec<T>(s, mid, hi, A, lda, Dinv, dinfo);
+}
+
 // Cholesky B = U^H U (upper, in place).  *info_h = 0 or the 1-based index of the first non-positive pivot.
 template <typename T>
 int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h) {
@@ -230,26 +294,13 @@ int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h) {
   if (n <= 0) return 0;
   if (enable_all_smem<T>() != 0) return -1;
   Context& c = ctx();
-  void* scr = ctx_scratch((size_t)NB * NB * sizeof(T) + 256);
+  const int nblk = cdiv(n, NB);
+  void* scr = ctx_scratch((size_t)nblk * NB * NB * sizeof(T) + 256);
   if (!scr) return -1;
   T* Dinv = (T*)scr;
   int* dinfo = c.d_info + 1;
   EIGB_CUDA_CHECK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
-  for (int k = 0; k < n; k += NB) {
-    const int nb = n - k < NB ? n - k : NB;
-    potf2_block_kernel<T><<<1, 256, blk_smem<T>(), s>>>(B, ldb, k, nb, Dinv, dinfo);
-    EIGB_LAUNCH_CHECK();
-    const int rest = n - k - nb;
-    if (rest > 0) {
-      // row panel: U(k, k+nb:) = U_kk^-H * A(k, k+nb:)
-      diag_mult_kernel<T, true, true><<<cdiv(rest, NB), 256, blk_smem<T>(), s>>>(Dinv, B, ldb, k, nb, k + nb, n);
-      EIGB_LAUNCH_CHECK();
-      // trailing update A22 -= U12^H U12 (upper)
-      T* U12 = B + k + (int64_t)(k + nb) * ldb;
-      if (herk_upper<T>(s, 'C', rest, nb, -1.0, U12, ldb, 1.0, B + (k + nb) + (int64_t)(k + nb) * ldb, ldb) != 0)
-        return -1;
-    }
-  }
+  if (potrf_rec<T>(s, 0, n, B, ldb, Dinv, dinfo) != 0) return -1;
   EIGB_CUDA_CHECK(cudaMemcpyAsync(info_h, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
   EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
   return 0;
@@ -264,45 +315,14 @@ int trsm_upper(cudaStream_t s, char side, char trans, int m, int n, const T* U, 
   if (m <= 0 || n <= 0) return 0;
   if (enable_all_smem<T>() != 0) return -1;
   const int nu = (side == 'L') ? m : n;
+  const int other = (side == 'L') ? n : m;
   const int nblk = cdiv(nu, NB);
   void* scr = ctx_scratch((size_t)nblk * NB * NB * sizeof(T) + 256);
   if (!scr) return -1;
   T* Dinv = (T*)scr;
   trtri_blocks_kernel<T><<<nblk, NB, blk_smem<T>(), s>>>(U, ldu, nu, Dinv);
   EIGB_LAUNCH_CHECK();
-  if (side == 'L' && trans == 'N') {
-    for (int b = nblk - 1; b >= 0; --b) {
-      const int r0 = b * NB, nb = nu - r0 < NB ? nu - r0 : NB;
-      diag_mult_kernel<T, true, false><<<cdiv(n, NB), 256, blk_smem<T>(), s>>>(Dinv + (int64_t)b * NB * NB, B, ldb, r0, nb, 0, n);
-      EIGB_LAUNCH_CHECK();
-      if (r0 > 0) {   // B(0:r0, :) -= U(0:r0, r0:r0+nb) * X_b
-        if (gemm<T>(s, 'N', 'N', r0, n, nb, -1.0, U + (int64_t)r0 * ldu, ldu, B + r0, ldb, 1.0, B, ldb) != 0) return -1;
-      }
-    }
-  } else if (side == 'L') {   // U^-H: forward
-    for (int b = 0; b < nblk; ++b) {
-      const int r0 = b * NB, nb = nu - r0 < NB ? nu - r0 : NB;
-      diag_mult_kernel<T, true, true><<<cdiv(n, NB), 256, blk_smem<T>(), s>>>(Dinv + (int64_t)b * NB * NB, B, ldb, r0, nb, 0, n);
-      EIGB_LAUNCH_CHECK();
-      const int rest = nu - r0 - nb;
-      if (rest > 0) {   // B(r0+nb:, :) -= U(r0:r0+nb, r0+nb:)^H * X_b
-        if (gemm<T>(s, 'C', 'N', rest, n, nb, -1.0, U + r0 + (int64_t)(r0 + nb) * ldu, ldu, B + r0, ldb, 1.0,
-                    B + r0 + nb, ldb) != 0) return -1;
-      }
-    }
-  } else {                    // right, no-trans: forward over column blocks
-    for (int b = 0; b < nblk; ++b) {
-      const int c0 = b * NB, nb = nu - c0 < NB ? nu - c0 : NB;
-      diag_mult_kernel<T, false, false><<<cdiv(m, NB), 256, blk_smem<T>(), s>>>(Dinv + (int64_t)b * NB * NB, B, ldb, c0, nb, 0, m);
-      EIGB_LAUNCH_CHECK();
-      const int rest = nu - c0 - nb;
-      if (rest > 0) {   // B(:, c0+nb:) -= X_b * U(c0:c0+nb, c0+nb:)
-        if (gemm<T>(s, 'N', 'N', m, rest, nb, -1.0, B + (int64_t)c0 * ldb, ldb, U + c0 + (int64_t)(c0 + nb) * ldu, ldu,
-                    1.0, B + (int64_t)(c0 + nb) * ldb, ldb) != 0) return -1;
-      }
-    }
-  }
-  return 0;
+  return trsm_rec<T>(s, side, trans, 0, nu, other, U, ldu, B, ldb, Dinv);
 }
 
 // Reduction to standard form A <- U^-H A U^-1 (zhegst_gpu.F90:31-109 / dsygst_gpu.F90:31-98).

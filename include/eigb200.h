@@ -41,6 +41,10 @@ int eigb200_prof_enable(int on);
 int eigb200_prof_reset(void);
 int eigb200_prof_collect(double* ms, int* cnt, long long* launches);
 
+/* profiling aid: with option "trd_trace"=1 the tridiagonalization records 5 globaltimer stamps (ns) per column
+ * (phase A start/end, after barrier, phase B end, after barrier); read them back here. Returns the count. */
+long long eigb200_trace_read(unsigned long long* out, long long max_count);
+
 /* ---- generalized drivers (the drop-in entry points) ------------------------------------------------ */
 /* dsygvdx_gpu(N,A,lda,B,ldb,Z,ldz,il,iu,w,work,lwork,work_h,lwork_h,iwork_h,liwork_h,Z_h,ldz_h,w_h,info,
  *             _skip_host_copy)                                       dsygvdx_gpu.F90:71-72 */
