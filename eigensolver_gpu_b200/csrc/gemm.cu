@@ -10,8 +10,8 @@ constexpr int STAGES = 3;    // cp.async ring depth
 constexpr int KPAD = 4;      // K-major smem row = BKT + 4 elements (conflict-free fragment reads)
 
 template <typename T> struct Cfg;
-template <> struct Cfg<double>  { static constexpr int BM = 128, BN = 128, WGM = 2, WGN = 4, PAD = 4; };
-template <> struct Cfg<double2> { static constexpr int BM = 128, BN = 64,  WGM = 4, WGN = 2, PAD = 2; };
+template <> struct Cfg<double>  { static constexpr int BM = 128, BN = 128, WGM = 4, WGN = 4, PAD = 4; };
+template <> struct Cfg<double2> { static constexpr int BM = 128, BN = 64,  WGM = 4, WGN = 4, PAD = 2; };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -64,7 +64,7 @@ __device__ __forceinline__ void load_tile(T* S, const T* __restrict__ G, int64_t
 }
 
 template <typename T, bool AK, bool BK, int CH>
-__global__ void __launch_bounds__(256) gemm_kernel(GemmParams<T> pv, const GemmParams<T>* __restrict__ dev) {
+__global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(GemmParams<T> pv, const GemmParams<T>* __restrict__ dev) {
   using C_ = Cfg<T>;
   constexpr int BM = C_::BM, BN = C_::BN, WGM = C_::WGM, WGN = C_::WGN, PAD = C_::PAD;
   constexpr int NT = WGM * WGN * 32;
@@ -214,7 +214,7 @@ int launch_one(cudaStream_t s, const GemmParams<T>& p, const GemmParams<T>* dev,
   int M = dev ? maxM : p.M, N = dev ? maxN : p.N;
   if (M <= 0 || N <= 0) return 0;
   dim3 grid(cdiv(M, C_::BM), cdiv(N, C_::BN), batch);
-  kern<<<grid, 256, SMEM, s>>>(p, dev);
+  kern<<<grid, C_::WGM * C_::WGN * 32, SMEM, s>>>(p, dev);
   EIGB_LAUNCH_CHECK();
   return 0;
 }
