@@ -13,6 +13,7 @@
 #include "gemm.cuh"
 #include "stages.cuh"
 #include <vector>
+#include <string.h>
 
 namespace eigb200 {
 
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) bt_finish_t_kernel(T* Tm_all, const T* __
 size_t ormtr_scratch_bytes(int n, int m, int esize) {
   int ib = opts().bt_nb < BTMAX ? opts().bt_nb : BTMAX;
   size_t nblk = (size_t)(n > 1 ? (n - 2) / ib + 1 : 1);
-  return ((size_t)n * n + nblk * BTMAX * BTMAX + 2 * (size_t)BTMAX * m) * esize + 8 * 256;
+  return ((size_t)n * n + nblk * BTMAX * BTMAX + 2 * (size_t)BTMAX * m) * esize + nblk * 256 + 8 * 256;
 }
 
 // Z(0:n, 0:m) <- Q Z.  A holds the reflectors (v_j in A(0:j, j+1), unit element explicit or not -- it is
@@ -97,14 +98,27 @@ int ormtr_upper(cudaStream_t s, int n, int m, const T* A, int64_t lda, const T* 
   T* Tm = ar.take<T>((size_t)nblk * BTMAX * BTMAX);
   T* X1 = ar.take<T>((size_t)BTMAX * m);
   T* X2 = ar.take<T>((size_t)BTMAX * m);
-  if (!X2) { set_last_error("ormtr: scratch arena exhausted"); return -1; }
+  GemmParams<T>* GP = ar.take<GemmParams<T>>(nblk);
+  if (!GP) { set_last_error("ormtr: scratch arena exhausted"); return -1; }
   bt_prepare_v_kernel<T><<<dim3(cdiv(n, 256), nref), 256, 0, s>>>(A, lda, n, ib, VW, ldv);
   EIGB_LAUNCH_CHECK();
-  // T0 = V^H V for every block (small outputs, long K)
-  for (int b = 0; b < nblk; ++b) {
-    const int j0 = b * ib, ibb = (nref - j0 < ib) ? nref - j0 : ib, mi = j0 + ibb;
-    if (gemm<T>(s, 'C', 'N', ibb, ibb, mi, 1.0, VW + (int64_t)j0 * ldv, ldv, VW + (int64_t)j0 * ldv, ldv, 0.0,
-                Tm + (int64_t)b * BTMAX * BTMAX, BTMAX) != 0) return -1;
+  // T0 = V^H V for every block (small outputs, long K): ONE batched launch, parameter blocks read from device memory
+  {
+    std::vector<GemmParams<T>> hp(nblk);
+    for (int b = 0; b < nblk; ++b) {
+      const int j0 = b * ib, ibb = (nref - j0 < ib) ? nref - j0 : ib, mi = j0 + ibb;
+      GemmParams<T>& q = hp[b];
+      memset(&q, 0, sizeof(q));
+      q.M = ibb; q.N = ibb; q.nseg = 1;
+      q.A[0] = VW + (int64_t)j0 * ldv; q.lda[0] = ldv; q.B[0] = q.A[0]; q.ldb[0] = ldv; q.K[0] = mi;
+      q.A[1] = q.A[0]; q.B[1] = q.B[0]; q.lda[1] = ldv; q.ldb[1] = ldv; q.K[1] = 0;
+      q.sa[0] = q.sa[1] = -1.0; q.sb[0] = q.sb[1] = 1.0;       // op(A) = V^H
+      q.C = Tm + (int64_t)b * BTMAX * BTMAX; q.ldc = BTMAX;
+      q.alpha = 1.0; q.beta = 0.0; q.mode = 0; q.real_diag = 0; q.colmap = nullptr;
+    }
+    EIGB_CUDA_CHECK(cudaMemcpyAsync(GP, hp.data(), sizeof(GemmParams<T>) * nblk, cudaMemcpyHostToDevice, s));
+    GemmParams<T> dummy{};
+    if (gemm_launch<T>(s, true, true, dummy, GP, nblk, ib, ib) != 0) return -1;
   }
   bt_finish_t_kernel<T><<<nblk, 256, 0, s>>>(Tm, tau, n, ib);
   EIGB_LAUNCH_CHECK();
