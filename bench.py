@@ -8,8 +8,9 @@ configuration the metric is quoted on) over synthetic family-R inputs (the refer
 A = T T^H, test_driver/test_zhegvdx.F90:28-66).  `value` is achieved GFLOP/s under the nominal flop model
 F(N,m) = k [(8/3) N^3 + 3 N^2 m], k = 4 for complex, inputs resident in HBM; `e2e` is the same
 metric through the reference-facing call with HOST buffers (H2D of A,B and D2H of Z,w inside the timed
-region).  N > 1: one process per GPU (torchrun), every rank solves its own problem (weak scaling, no
-data-path collective yet -- see DESIGN.md multi-GPU section).
+region).  N > 1: one process per GPU (torchrun), ONE problem solved by all ranks (strong scaling):
+eigensolver_gpu_b200/multi_gpu.py -- column-split solves/back-transform with NCCL exchanges, replicated
+deterministic potrf/hetrd/stedc (DESIGN.md multi-GPU section).
 """
 import argparse
 import json
@@ -127,10 +128,12 @@ def metric_name(args):
 def workload_config(args):
     return {"workload": f"{'ZHEGVDX' if args.dtype == 'z' else 'DSYGVDX'} N={args.n} il=1 iu={args.m} "
                         f"({'complex' if args.dtype == 'z' else 'real'} FP64, ITYPE=1 JOBZ=V RANGE=I UPLO=U)",
-            "inputs": "family R (reference recipe A=T*T^H, B=T*T^H), seed 1234+rank",
+            "inputs": "family R (reference recipe A=T*T^H, B=T*T^H), seed 1234 (same problem on every rank)",
             "l2": "inputs (N^2*16 B each) larger than the 126 MB L2; A,B restored from pristine device copies "
                   "inside the timed region (2 D2D copies per step)",
-            "parallelism": "replicas" if args.gpus > 1 else "single"}
+            "parallelism": ("1 problem over %d GPUs: potrf/hetrd/stedc replicated (bitwise deterministic), hegst solves, "
+                            "back-transform and final trsm split by columns + NCCL exchanges" % args.gpus)
+            if args.gpus > 1 else "single"}
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -173,7 +176,7 @@ def main():
     dt = torch.complex128 if cplx else torch.float64
     es = 16 if cplx else 8
     # synthetic family-R inputs generated on the device from a seeded generator (reference recipe)
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    gen = torch.Generator(device="cuda").manual_seed(1234)     # every rank builds the same problem
 
     def herm_uniform():
         t = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=gen)
@@ -202,17 +205,31 @@ def main():
     a_host.copy_(a0)
     b_host.copy_(b0)
 
+    if world > 1:
+        from eigensolver_gpu_b200 import multi_gpu as MG
+        mg_backend = MG.CudaStages()
+
     def step_device():
         A.copy_(a0)
         B.copy_(b0)
-        info, w, z, _ = api.solve_generalized(A, B, 1, m, ws=ws, skip_host_copy=True)
+        if world > 1:
+            info, w, z = MG.hegvdx_distributed(A, B, 1, m, backend=mg_backend, gather_z=True)
+        else:
+            info, w, z, _ = api.solve_generalized(A, B, 1, m, ws=ws, skip_host_copy=True)
         if info != 0:
             raise SystemExit("solve failed: " + lib.eigb200_last_error().decode())
 
     def step_e2e():
         A.copy_(a_host, non_blocking=True)
         B.copy_(b_host, non_blocking=True)
-        info, w, z, _ = api.solve_generalized(A, B, 1, m, ws=ws, skip_host_copy=False)   # D2H of Z(:,1:m), w inside
+        if world > 1:
+            info, w, z = MG.hegvdx_distributed(A, B, 1, m, backend=mg_backend, gather_z=True)
+            if rank == 0:
+                ws.Z_h[:m].copy_(z)
+                ws.w_h.copy_(w)
+                torch.cuda.synchronize()
+        else:
+            info, w, z, _ = api.solve_generalized(A, B, 1, m, ws=ws, skip_host_copy=False)   # D2H of Z(:,1:m), w inside
         if info != 0:
             raise SystemExit("solve failed: " + lib.eigb200_last_error().decode())
 
@@ -251,12 +268,12 @@ def main():
     lib.eigb200_prof_enable(0)
     ms_step = ms_total / args.steps
     fl = flops_model(n, m, cplx)
-    value = world * fl / (ms_step * 1e-3) * 1e-9
+    value = fl / (ms_step * 1e-3) * 1e-9            # one problem, solved by all ranks together
 
     # end-to-end through the reference-facing call with host buffers
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
-    e2e_val = world * fl / (ms_e2e * 1e-3) * 1e-9
+    e2e_val = fl / (ms_e2e * 1e-3) * 1e-9
     h2d = 2 * n * n * es
     d2h = n * m * es + n * 8
 
@@ -287,7 +304,8 @@ def main():
                 "avg_launch_ms": panel_ms_per_solve / panel_launches}
     line = {
         "metric": metric_name(args), "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "c128" if cplx else "f64", "data": "synthetic",
         "config": workload_config(args),
         "clocks": clocks,

@@ -79,34 +79,41 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(T* A, int64_t lda, int
     s[r + c * (NB + 1)] = (r <= c) ? A[(r0 + r) + (int64_t)(r0 + c) * lda] : zero_<T>();
   }
   __syncthreads();
+  // outer-product Cholesky with ONE barrier per step: row j is used unscaled (a_il -= conj(a_ji) a_jl / a_jj) and the
+  // 1/sqrt(pivot) scaling of the rows is applied in a single pass at the end (a_jj is final after step j)
   for (int j = 0; j < nb; ++j) {
     const double piv = real_(s[j + j * (NB + 1)]);
     if (!(piv > 0.0)) { if (tid == 0 && bad == 0) bad = r0 + j + 1; }
-    const double rp = sqrt(piv), irp = 1.0 / rp;
-    __syncthreads();
-    // scale row j
-    for (int c = j + tid; c < nb; c += blockDim.x)
-      s[j + c * (NB + 1)] = (c == j) ? from_real<T>(rp) : scale_(s[j + c * (NB + 1)], irp);
-    __syncthreads();
-    // trailing update a(i,l) -= conj(u(j,i)) u(j,l), j < i <= l
+    const double ipiv = 1.0 / piv;
     const int m = nb - j - 1;
     for (int idx = tid; idx < m * m; idx += blockDim.x) {
       const int i = j + 1 + idx % m, l = j + 1 + idx / m;
       if (i <= l) {
         T t = zero_<T>();
         fmac_(t, s[j + i * (NB + 1)], s[j + l * (NB + 1)]);
-        s[i + l * (NB + 1)] = sub_(s[i + l * (NB + 1)], t);
+        s[i + l * (NB + 1)] = sub_(s[i + l * (NB + 1)], scale_(t, ipiv));
       }
     }
     __syncthreads();
   }
   for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
     const int r = idx % nb, c = idx / nb;
-    if (r <= c) {
-      T v = s[r + c * (NB + 1)];
-      if (r == c) v = from_real<T>(real_(v));
-      A[(r0 + r) + (int64_t)(r0 + c) * lda] = v;
+    if (r < c) {
+      const double rs = 1.0 / sqrt(real_(s[r + r * (NB + 1)]));
+      inv[r + c * (NB + 1)] = scale_(s[r + c * (NB + 1)], rs);     // staged in `inv` (diagonal still needed unscaled)
     }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+    const int r = idx % nb, c = idx / nb;
+    if (r < c) s[r + c * (NB + 1)] = inv[r + c * (NB + 1)];
+  }
+  __syncthreads();
+  if (tid < nb) s[tid + tid * (NB + 1)] = from_real<T>(sqrt(real_(s[tid + tid * (NB + 1)])));
+  __syncthreads();
+  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+    const int r = idx % nb, c = idx / nb;
+    if (r <= c) A[(r0 + r) + (int64_t)(r0 + c) * lda] = s[r + c * (NB + 1)];
   }
   tri_inverse_smem<T>(s, inv, nb);
   __syncthreads();
@@ -326,15 +333,50 @@ int trsm_upper(cudaStream_t s, char side, char trans, int m, int n, const T* U, 
 }
 
 // Reduction to standard form A <- U^-H A U^-1 (zhegst_gpu.F90:31-109 / dsygst_gpu.F90:31-98).
-// A's upper triangle is read; on exit the full Hermitian result is stored (both triangles).  The caller's
-// strict lower triangle of A is saved into `save` first when save != nullptr (the reference keeps it in Z,
-// zhegvdx_gpu.F90:145-152).
+// A's upper triangle is read; on exit the upper triangle holds the result (diagonal blocks are full Hermitian,
+// as in the reference).  The caller's strict lower triangle of A is saved into `save` first when save != nullptr
+// (the reference keeps it in Z, zhegvdx_gpu.F90:145-152).
+//
+// Same blocked algorithm as the reference / LAPACK ?hegst(1,'U') -- k N^3 flops, half of the "two full TRSM"
+// formulation -- with block size 1024-2048 and every solve done by the recursive TRSM above:
+//   A_kk <- U_kk^-H herm(A_kk) U_kk^-1 ;  A_k* <- U_kk^-H A_k* ;  A_k* -= 1/2 A_kk U_k* ;
+//   A_** -= A_k*^H U_k* + U_k*^H A_k* ;   A_k* -= 1/2 A_kk U_k* ;  A_k* <- A_k* U_**^-1
 template <typename T>
 int hegst_upper(cudaStream_t s, int n, T* A, int64_t lda, const T* U, int64_t ldu, T* save, int64_t lds) {
   if (n <= 0) return 0;
-  if (symmetrize_from_upper<T>(s, n, A, lda, save, lds) != 0) return -1;
-  if (trsm_upper<T>(s, 'L', 'C', n, n, U, ldu, A, lda) != 0) return -1;
-  if (trsm_upper<T>(s, 'R', 'N', n, n, U, ldu, A, lda) != 0) return -1;
+  if (enable_all_smem<T>() != 0) return -1;
+  if (save) {
+    // save tril(A) (the diagonal blocks get overwritten below); symmetrize_kernel with a save area also mirrors,
+    // which is harmless: only the upper triangle is read afterwards
+    if (symmetrize_from_upper<T>(s, n, A, lda, save, lds) != 0) return -1;
+  }
+  const int nblk = cdiv(n, NB);
+  void* scr = ctx_scratch((size_t)nblk * NB * NB * sizeof(T) + 256);
+  if (!scr) return -1;
+  T* Dinv = (T*)scr;
+  trtri_blocks_kernel<T><<<nblk, NB, blk_smem<T>(), s>>>(U, ldu, n, Dinv);
+  EIGB_LAUNCH_CHECK();
+  const int HB = (n >= 4096) ? 2048 : 1024;
+  for (int k = 0; k < n; k += HB) {
+    const int kb = n - k < HB ? n - k : HB;
+    const int r = n - k - kb;
+    T* Akk = A + k + (int64_t)k * lda;
+    // diagonal block: complete it, then two-sided solve restricted to [k, k+kb)
+    symmetrize_kernel<T><<<dim3(cdiv(kb, 256), kb), 256, 0, s>>>(Akk, lda, kb, (T*)nullptr, 0);
+    EIGB_LAUNCH_CHECK();
+    if (trsm_rec<T>(s, 'L', 'C', k, k + kb, kb, U, ldu, A + (int64_t)k * lda, lda, Dinv) != 0) return -1;
+    if (trsm_rec<T>(s, 'R', 'N', k, k + kb, kb, U, ldu, A + k, lda, Dinv) != 0) return -1;
+    if (r > 0) {
+      T* Akr = A + k + (int64_t)(k + kb) * lda;            // A_k*  (kb x r)
+      const T* Ukr = U + k + (int64_t)(k + kb) * ldu;      // U_k*
+      T* Arr = A + (k + kb) + (int64_t)(k + kb) * lda;     // A_**
+      if (trsm_rec<T>(s, 'L', 'C', k, k + kb, r, U, ldu, A + (int64_t)(k + kb) * lda, lda, Dinv) != 0) return -1;
+      if (gemm<T>(s, 'N', 'N', kb, r, kb, -0.5, Akk, lda, Ukr, ldu, 1.0, Akr, lda) != 0) return -1;
+      if (her2k_upper<T>(s, 'C', r, kb, -1.0, Akr, lda, Ukr, ldu, 1.0, Arr, lda) != 0) return -1;
+      if (gemm<T>(s, 'N', 'N', kb, r, kb, -0.5, Akk, lda, Ukr, ldu, 1.0, Akr, lda) != 0) return -1;
+      if (trsm_rec<T>(s, 'R', 'N', k + kb, n, kb, U, ldu, A + k, lda, Dinv) != 0) return -1;
+    }
+  }
   return 0;
 }
 

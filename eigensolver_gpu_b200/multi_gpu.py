@@ -1,0 +1,113 @@
+"""Multi-GPU driver for the generalized eigensolve: one process per GPU, `torch.distributed` (NCCL) plumbing.
+
+Round-1 partition: every stage whose right-hand sides are independent is split 1-D by
+columns across the ranks -- the two triangular solves of the reduction to standard form (`U^-H A`, then
+`U^-H Y^H` using C = C^H), the back-transformation `Z <- Q Z` and the final `Z <- U^-1 Z` -- each followed by
+one exchange of the column blocks.  The Cholesky factorization, the tridiagonalization and the tridiagonal
+divide & conquer run replicated; they are bitwise deterministic (no atomics), so all ranks hold identical
+`U`, reflectors and tridiagonal eigenvectors without any broadcast.  The 1-D block-column distribution of
+the trailing matrix inside the tridiagonalization (per-column all-reduce of `w`) is the next step.
+
+The orchestration is written against a small "stage backend" so that the partition / exchange logic is
+exercised on CPU with the gloo backend (tests/test_multi_gpu_cpu.py) while the product uses the CUDA stages.
+"""
+import torch
+import torch.distributed as dist
+
+
+def column_ranges(ncols, world, align=64):
+    """Contiguous column ranges [c0, c1) per rank, boundaries aligned to `align` (the TRSM/tile block size)."""
+    nblk = (ncols + align - 1) // align
+    out = []
+    for r in range(world):
+        b0 = (nblk * r) // world
+        b1 = (nblk * (r + 1)) // world
+        out.append((min(b0 * align, ncols), min(b1 * align, ncols)))
+    return out
+
+
+class CudaStages:
+    """The product backend: hand-written CUDA stages through the C ABI."""
+
+    def __init__(self):
+        from . import stages as S
+        self.S = S
+
+    def potrf(self, b):
+        return self.S.potrf(b)
+
+    def trsm_left(self, trans, u, cols):            # cols: tensor (ncols, n) = column block, solved in place
+        if cols.shape[0] > 0:
+            self.S.trsm("L", trans, u, cols, m=u.shape[0], n=cols.shape[0])
+
+    def hetrd(self, a):
+        return self.S.hetrd(a)
+
+    def stedc(self, d, e):
+        return self.S.stedc(d, e)
+
+    def ormtr(self, a, tau, zcols):
+        if zcols.shape[0] > 0:
+            self.S.ormtr(a, tau, zcols, m=zcols.shape[0])
+
+    def symmetrize_from_upper(self, a):
+        n = a.shape[0]
+        # a is (cols, rows) = column-major A; upper triangle of A = entries with row <= col = a[c, r], r <= c
+        low = torch.tril(a)                          # as a (c, r) array: r <= c  -> upper triangle of A
+        full = low + torch.tril(a, -1).conj().T
+        if full.is_complex():
+            idx = torch.arange(n, device=a.device)
+            full[idx, idx] = full[idx, idx].real.to(full.dtype)
+        return full.contiguous()
+
+
+def _exchange_columns(x, ranges, group):
+    """x: (ncols, n) column-major matrix; every rank owns rows ranges[rank] of x (= a column block of the
+    matrix). After the call all ranks hold all blocks."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    for r, (c0, c1) in enumerate(ranges):
+        if c1 > c0:
+            blk = x[c0:c1]
+            dist.broadcast(blk, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+
+
+def hegvdx_distributed(a, b, il, iu, backend=None, group=None, gather_z=True):
+    """Distributed A x = lambda B x, il..iu (1-based).  a, b: column-major device tensors (shape (n, n) holding
+    the transposed view, see stages.to_dev), identical on all ranks, upper triangles used; both overwritten.
+    Returns (info, w[all n], Z) with Z of shape (m, n) = m eigenvector columns (all of them on every rank if
+    gather_z, else only this rank's column block, others zero)."""
+    be = backend or CudaStages()
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n = a.shape[0]
+    m = iu - il + 1
+    # 1. Cholesky, replicated (deterministic)
+    info = be.potrf(b)
+    if info != 0:
+        return -1, None, None
+    # 2. C = U^-H A U^-1 by two column-parallel left solves: Y = U^-H A, then C^H = U^-H Y^H (C = C^H)
+    y = be.symmetrize_from_upper(a)
+    rng = column_ranges(n, world)
+    c0, c1 = rng[rank]
+    be.trsm_left("C", b, y[c0:c1])
+    _exchange_columns(y, rng, group)
+    yh = y.conj().T.contiguous() if y.is_complex() else y.T.contiguous()   # column-major Y^H
+    be.trsm_left("C", b, yh[c0:c1])
+    _exchange_columns(yh, rng, group)
+    a.copy_(yh)                      # = C^H = C (full Hermitian, both triangles)
+    # 3. tridiagonalization + divide & conquer, replicated (deterministic)
+    d, e, tau = be.hetrd(a)
+    w, q = be.stedc(d, e)
+    # 4. back-transformation and final triangular solve on this rank's eigenvector columns
+    z = torch.zeros((m, n), dtype=a.dtype, device=a.device)
+    zr = column_ranges(m, world)
+    z0, z1 = zr[rank]
+    if z1 > z0:
+        z[z0:z1] = q[il - 1 + z0:il - 1 + z1].to(a.dtype)
+        be.ormtr(a, tau, z[z0:z1])
+        be.trsm_left("N", b, z[z0:z1])
+    if gather_z:
+        _exchange_columns(z, zr, group)
+    return 0, w, z
