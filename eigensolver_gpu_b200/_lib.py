@@ -20,6 +20,9 @@ SIGNATURES = {
     "eigb200_set_stream": (_i, [_p]),
     "eigb200_version": (_i, []),
     "eigb200_scratch_bytes": (C.c_int64, [_i, _i]),
+    "eigb200_mg_alloc": (_i, [C.c_longlong, C.POINTER(C.c_void_p), C.c_char_p]),
+    "eigb200_mg_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "eigb200_mg_config": (_i, [_i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_longlong, _p]),
     "eigb200_prof_enable": (_i, [_i]),
     "eigb200_prof_reset": (_i, []),
     "eigb200_prof_collect": (_i, [_p, _p, _p]),

@@ -25,6 +25,36 @@ const char* eigb200_last_error(void) { return last_error(); }
 int eigb200_set_stream(void* s) { ctx().stream = (cudaStream_t)s; return 0; }
 int eigb200_version(void) { return 100; }
 
+// ---- multi-GPU plumbing for the distributed tridiagonalization -------------------------------------------------
+int eigb200_mg_alloc(long long bytes, void** dptr, char* handle64) {
+  API_BEGIN();
+  void* p = nullptr;
+  EIGB_CUDA_CHECK(cudaMalloc(&p, (size_t)bytes));
+  EIGB_CUDA_CHECK(cudaMemset(p, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  EIGB_CUDA_CHECK(cudaIpcGetMemHandle(&h, p));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *dptr = p;
+  return 0;
+}
+int eigb200_mg_open(const char* handle64, void** dptr) {
+  API_BEGIN();
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  EIGB_CUDA_CHECK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int eigb200_mg_config(int rank, int world, void** wbufs, void** flags, long long wbuf_bytes, void* panel_hook) {
+  API_BEGIN();
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) { set_last_error("eigb200_mg_config: bad rank/world"); return -1; }
+  MgConfig& M = mg();
+  M.rank = rank; M.P = world; M.wbuf_bytes = wbuf_bytes;
+  for (int q = 0; q < world; ++q) { M.wbuf[q] = wbufs ? wbufs[q] : nullptr; M.flags[q] = flags ? (unsigned long long*)flags[q] : nullptr; }
+  M.hook = (panel_hook_t)panel_hook;
+  return 0;
+}
+
 int eigb200_prof_enable(int on) { prof_enable(on); return 0; }
 int eigb200_prof_reset(void) { prof_reset(); return 0; }
 int eigb200_prof_collect(double* ms, int* cnt, long long* launches) { prof_collect(ms, cnt, launches); return 0; }

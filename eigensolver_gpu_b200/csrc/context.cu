@@ -123,6 +123,7 @@ void prof_collect(double* ms, int* cnt, long long* launches) {
 }
 
 Options& opts() { static Options o; return o; }
+MgConfig& mg() { static MgConfig m; return m; }
 int set_option(const char* name, int value) {
   Options& o = opts();
   if (!strcmp(name, "trd_nb")) { if (value < 1 || value > 128) return -1; o.trd_nb = value; return 0; }
@@ -130,6 +131,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "symv_tma")) { o.symv_tma = value; return 0; }
   if (!strcmp(name, "trd_coop")) { o.trd_coop = value; return 0; }
   if (!strcmp(name, "trd_trace")) { o.trd_trace = value; return 0; }
+  if (!strcmp(name, "mg_switch_n")) { o.mg_switch_n = value; return 0; }
   if (!strcmp(name, "verbose")) { ctx().verbose = value; return 0; }
   return -1;
 }
@@ -139,6 +141,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "bt_nb")) return o.bt_nb;
   if (!strcmp(name, "symv_tma")) return o.symv_tma;
   if (!strcmp(name, "trd_coop")) return o.trd_coop;
+  if (!strcmp(name, "mg_switch_n")) return o.mg_switch_n;
   if (!strcmp(name, "verbose")) return ctx().verbose;
   return -1;
 }

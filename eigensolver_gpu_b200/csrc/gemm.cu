@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(Ge
   GemmParams<T> p = dev ? dev[blockIdx.z] : pv;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (m0 >= p.M || n0 >= p.N) return;
-  if (p.mode == 1 && m0 > n0 + BN - 1) return;   // tile strictly below the diagonal
+  if (p.mode == 1 && m0 > n0 + BN - 1 + p.diag_off) return;   // tile strictly below the diagonal
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm0 = (warp % WGM) * WTM, wn0 = (warp / WGM) * WTN;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(Ge
       for (int r = 0; r < 2; ++r) {
         const int gn = n0 + wn0 + j * 8 + 2 * t + r;
         if (gn >= p.N) continue;
-        if (p.mode == 1 && gm > gn) continue;
+        if (p.mode == 1 && gm > gn + p.diag_off) continue;
         const int cn = p.colmap ? p.colmap[gn] : gn;
         T* cp = p.C + gm + (int64_t)cn * p.ldc;
         if constexpr (!CPLX) {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(Ge
         } else {
           double2 v = mkz(alpha * acc[i][j][r], alpha * acc[i][j][2 + r]);
           if (beta != 0.0) { double2 o = *cp; v.x += beta * o.x; v.y += beta * o.y; }
-          if (p.real_diag && gm == gn) v.y = 0.0;
+          if (p.real_diag && gm == gn + p.diag_off) v.y = 0.0;
           *cp = v;
         }
       }

@@ -25,6 +25,7 @@ struct GemmParams {
   int mode;                 // 0: full C, 1: upper triangle of C only (row <= col)
   int real_diag;            // complex + mode 1: force Im C(i,i) = 0
   const int* colmap;        // optional: output column gn is stored at column colmap[gn] of C
+  int diag_off;             // mode 1: element (gm, gn) is written iff gm <= gn + diag_off (C is a column block)
 };
 
 // op(A)(m,k): AK=false -> A[m + k*lda] ('N');  AK=true -> A[k + m*lda] ('T'/'C', conj via sa=-1)

@@ -15,9 +15,22 @@ struct Options {
   int bt_nb = 128;      // back-transformation block (reference: 64, zheevd_gpu.F90:64)
   int symv_tma = 1;     // stage symv/hemv tiles through TMA (cp.async.bulk.tensor) when alignment allows
   int trd_coop = 1;     // persistent cooperative panel kernel (0: one launch per phase)
+  int mg_switch_n = 3072; // multi-GPU hetrd: below this trailing order all ranks continue replicated
   int trd_trace = 0;    // record per-column globaltimer stamps of the panel kernel (profiling aid)
 };
 Options& opts();
+
+// multi-GPU configuration of the tridiagonalization (set through eigb200_mg_config)
+typedef void (*panel_hook_t)(int i0, int nbp, int owner);
+struct MgConfig {
+  int rank = 0, P = 1;
+  void* wbuf[8] = {nullptr};              // exchange buffers of all ranks (peer-mapped), wbuf[rank] is local
+  unsigned long long* flags[8] = {nullptr};
+  int64_t wbuf_bytes = 0;                 // size of ONE rank's exchange buffer
+  unsigned long long seq = 0;             // monotonic column sequence number (flags never reset)
+  panel_hook_t hook = nullptr;            // called before every panel: broadcast of the panel's columns from `owner`
+};
+MgConfig& mg();
 }
 #include <vector>
 namespace eigb200 {

@@ -70,6 +70,12 @@ struct TrdP {
   int vec_ok;                  // 16-byte loads allowed (real: A 16B aligned and lda even)
   int use_tma;                 // off-diagonal tiles staged through the TMA ring (needs vec_ok)
   unsigned long long* trace;   // optional: 5 globaltimer stamps per column (CTA 0), profiling aid
+  // multi-GPU (1-D block-cyclic distribution of the 64-wide tile columns of the trailing matrix over P ranks)
+  int rank, P;                 // P == 1: single GPU
+  T* peer_w[8];                // peer_w[q] = rank q's exchange buffer [P][2][wstride] (peer-mapped, NVLink)
+  unsigned long long* peer_flag[8];   // peer_flag[q] = rank q's arrival flags [P]
+  int64_t wstride;             // elements per exchange slot (>= n + 2)
+  unsigned long long seq_base; // sequence number of this panel's first column (flags are monotonic)
 };
 
 // per-thread pipeline state of the tile ring; persists across columns inside the cooperative kernel.
@@ -128,10 +134,10 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
 }
 
 // ---- grid barrier (monotonic counter, watchdog-protected) --------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int* status) {
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int* status, bool sys = false) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (sys) __threadfence_system(); else __threadfence();
     atomicAdd(bar, 1u);
     unsigned long long spins = 0;
     while (true) {
@@ -164,9 +170,9 @@ __host__ __device__ __forceinline__ int zchunk_rows(int n) {
 }
 
 // tiles per strip chunk for an order-n product on G CTAs: aim at >= 6 units per CTA, at most 8 tiles per unit
-__host__ __device__ __forceinline__ int strip_len(int n, int G) {
+__host__ __device__ __forceinline__ int strip_len(int n, int G, int P = 1) {
   const int Tn = (n + TB - 1) / TB;
-  int c = (Tn * (Tn - 1) / 2) / (6 * G);
+  int c = (Tn * (Tn - 1) / 2) / (6 * G * P);
   if (c < 1) c = 1;
   if (c > 8) c = 8;
   return c;
@@ -212,24 +218,38 @@ __device__ __forceinline__ void larfg_scalars(double2 alpha, double xnorm2, doub
 // conflict-free shared-memory loads (or from global memory with 128-bit loads when the ring is off).
 // =====================================================================================================
 struct TileIter {
-  int unit, G, NF, total, Tn, C;
+  int unit, G, NF, total, Tn, C, rank, P, TnO;
   int J, I1, cur, band;
   bool has_diag, done;
+  // owned tile columns are J = rank + P*jj, jj = 0..TnO-1
+  __device__ __forceinline__ int first_owned_at_least(int Jmin) const {   // smallest jj with rank + P*jj >= Jmin
+    const int d = Jmin - rank;
+    return d <= 0 ? 0 : (d + P - 1) / P;
+  }
   __device__ __forceinline__ void load_unit() {
     if (unit >= total) { done = true; return; }
     if (unit < NF) {
       int u = unit, k = 0;
-      while (true) { const int cnt = Tn - (k + 1) * C; if (u < cnt) break; u -= cnt; ++k; }
-      band = k; J = (k + 1) * C + u; cur = k * C; I1 = k * C + C; has_diag = false;
+      while (true) {
+        const int jj0 = first_owned_at_least((k + 1) * C);
+        const int cnt = TnO - jj0 > 0 ? TnO - jj0 : 0;
+        if (u < cnt) { J = rank + P * (jj0 + u); break; }
+        u -= cnt; ++k;
+      }
+      band = k; cur = k * C; I1 = k * C + C; has_diag = false;
     } else {
-      J = unit - NF; band = J / C; cur = band * C; I1 = J; has_diag = true;
+      J = rank + P * (unit - NF); band = J / C; cur = band * C; I1 = J; has_diag = true;
     }
   }
-  __device__ __forceinline__ void init(int cta, int G_, int Tn_, int C_) {
-    G = G_; Tn = Tn_; C = C_; done = false;
+  __device__ __forceinline__ void init(int cta, int G_, int Tn_, int C_, int rank_ = 0, int P_ = 1) {
+    G = G_; Tn = Tn_; C = C_; rank = rank_; P = P_; done = false;
+    TnO = rank < Tn ? (Tn - rank + P - 1) / P : 0;
     NF = 0;
-    for (int k = 0; Tn - (k + 1) * C > 0; ++k) NF += Tn - (k + 1) * C;
-    total = NF + Tn;
+    for (int k = 0; (k + 1) * C < Tn; ++k) {
+      const int jj0 = first_owned_at_least((k + 1) * C);
+      NF += TnO - jj0 > 0 ? TnO - jj0 : 0;
+    }
+    total = NF + TnO;
     unit = cta;
     load_unit();
   }
@@ -302,13 +322,14 @@ __device__ __forceinline__ void warp_reduce4(double2 (&v)[4], int lane) {
 template <typename T, class XR>
 __device__ double tile_engine(const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc, XR xfix, T* Pd,
                               T* Pt, int64_t ldp, int cta, int G, int C, bool tma, int vec_ok, T* ring, uint64_t* full,
-                              uint64_t* empty, RingState& rs, EngineSmem<T>& es, const CUtensorMap* tmap) {
+                              uint64_t* empty, RingState& rs, EngineSmem<T>& es, const CUtensorMap* tmap, int rank = 0,
+                              int P = 1) {
   constexpr int S = RingCfg<T>::STAGES, NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Tn = (n + TB - 1) / TB;
   double vav = 0.0;
   TileIter it;
-  it.init(cta, G, Tn, C);
+  it.init(cta, G, Tn, C, rank, P);
   int I, J, band; bool diag, first, last;
 
   if (warp >= NW) {
@@ -440,6 +461,26 @@ __device__ __forceinline__ T gather_partials(const T* Pd, const T* Pt, int64_t l
   return add_(s0, s1);
 }
 
+// ---- multi-GPU exchange helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" :: "l"(p), "l"(v) : "memory");
+}
+// sequence number of the exchange that follows the product of panel column c
+template <typename T>
+__device__ __forceinline__ unsigned long long col_seq(const TrdP<T>& p, int c) {
+  return p.seq_base + (unsigned long long)(p.nbp - 1 - c) + 1ull;
+}
+// this rank's slot for source rank q and parity par in the exchange buffer of rank `dst`
+template <typename T>
+__device__ __forceinline__ T* ex_slot(const TrdP<T>& p, int dst, int q, unsigned par) {
+  return p.peer_w[dst] + ((int64_t)q * 2 + par) * p.wstride;
+}
+
 // ---- stand-alone symv/hemv (eigb200_dsymv / eigb200_zhemv): the same engine + a gather kernel -------------
 template <typename T>
 __global__ void __launch_bounds__(NTT, 1) hemv_tiles_kernel(const __grid_constant__ CUtensorMap tmap,
@@ -479,9 +520,23 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
   const int jp = j + 1;                         // order of the product done for column c+1
   const bool have_prev = (c + 1 <= nbp - 1) && (jp >= 1) && !(c == -1 && p.i0 == 0);
   const int cprev = c + 1;
-  const int Cp = strip_len(jp, G);              // strip length used by the previous phase B
+  const int Cp = strip_len(jp, G, p.P);         // strip length used by the previous phase B
   T tau_p = zero_<T>();
   double alpha_p = 0.0;
+  const bool mg = p.P > 1;
+  const unsigned long long seqp = have_prev ? col_seq(p, cprev) : 0ull;
+  const unsigned parp = (unsigned)(seqp & 1ull);
+  if (mg && have_prev) {
+    // wait until every rank has delivered its partial w (and v^H A v) of the previous column
+    if (tid < p.P) {
+      const unsigned long long* fl = p.peer_flag[p.rank] + tid;
+      unsigned long long spins = 0;
+      while (ld_acquire_sys(fl) < seqp) {
+        if (++spins > (1ull << 26)) { atomicExch(p.status, 78); break; }
+      }
+    }
+    __syncthreads();
+  }
 
   if (have_prev) {
     // -- z1 = V^H v, z2 = W^H v from the row-chunk partials; v^H A v from the per-CTA partials
@@ -508,7 +563,8 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
     }
     if (tid == 0) sm.u.a.rowV[cprev] = from_real<T>(1.0);   // unit element of v_{c+1} sits in row j
     double vv = 0.0;
-    for (int g = tid; g < G; g += NT) vv += __ldcg(p.vavpart + g);
+    if (!mg) { for (int g = tid; g < G; g += NT) vv += __ldcg(p.vavpart + g); }
+    else if (tid < p.P) vv = real_(ldcg_(ex_slot(p, p.rank, tid, parp) + p.wstride - 1));
     vv = block_sum<double>(vv, sm.dscal);    // (contains __syncthreads: z1/z2/rowV/rowW visible after it)
     // rho = v^H A v - 2 Re(z1^H z2)
     double zz = 0.0;
@@ -533,8 +589,12 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
       // wraw_j: lane-strided gather of the partials of row j, fixed order
       const int Tn = (jp + TB - 1) / TB, I = j / TB;
       T wr = zero_<T>();
-      for (int J = I + 1 + lane; J < Tn; J += 32) wr = add_(wr, ldcg_(p.Pd + (int64_t)J * p.ldp + j));
-      for (int k = lane; k <= I / Cp; k += 32) wr = add_(wr, ldcg_(p.Pt + (int64_t)k * p.ldp + j));
+      if (!mg) {
+        for (int J = I + 1 + lane; J < Tn; J += 32) wr = add_(wr, ldcg_(p.Pd + (int64_t)J * p.ldp + j));
+        for (int k = lane; k <= I / Cp; k += 32) wr = add_(wr, ldcg_(p.Pt + (int64_t)k * p.ldp + j));
+      } else if (lane < p.P) {
+        wr = ldcg_(ex_slot(p, p.rank, lane, parp) + j);
+      }
       wr = warp_sum(wr);
       if (lane == 0) {
         T w = mul_(tau_p, sub_(wr, part));
@@ -563,12 +623,16 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
           if (c >= 0) { fma_(t2, vv, conj_(sm.u.a.rowW[cc])); fma_(t2, ww, conj_(sm.u.a.rowV[cc])); }
         }
         if (have_prev) {
-          const int I = (g * 32) / TB;
-          const int nd = Tn - (I + 1);                // direct slots J = I+1 .. Tn-1
-          const int nt = I / Cp + 1;                  // band slots k = 0 .. I/Cp
-          for (int q = warp; q < nd + nt; q += AW) {
-            const T* src = (q < nd) ? (p.Pd + (int64_t)(I + 1 + q) * p.ldp) : (p.Pt + (int64_t)(q - nd) * p.ldp);
-            wr = add_(wr, ldcg_(src + r));
+          if (!mg) {
+            const int I = (g * 32) / TB;
+            const int nd = Tn - (I + 1);                // direct slots J = I+1 .. Tn-1
+            const int nt = I / Cp + 1;                  // band slots k = 0 .. I/Cp
+            for (int q = warp; q < nd + nt; q += AW) {
+              const T* src = (q < nd) ? (p.Pd + (int64_t)(I + 1 + q) * p.ldp) : (p.Pt + (int64_t)(q - nd) * p.ldp);
+              wr = add_(wr, ldcg_(src + r));
+            }
+          } else {
+            for (int q = warp; q < p.P; q += AW) wr = add_(wr, ldcg_(ex_slot(p, p.rank, q, parp) + r));
           }
         }
       }
@@ -661,10 +725,59 @@ __device__ void phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, Ring
   }
   // -- the tile engine: w_raw partials and v^H A v
   __syncthreads();     // phase-A scratch is dead from here on: the engine overlays it
-  double vav = tile_engine<T>(p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, cta, G, strip_len(j, G), p.use_tma != 0,
-                              p.vec_ok, ring, sm.full, sm.empty, rs, sm.u.e, tmap);
+  double vav = tile_engine<T>(p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, cta, G, strip_len(j, G, p.P),
+                              p.use_tma != 0, p.vec_ok, ring, sm.full, sm.empty, rs, sm.u.e, tmap, p.rank, p.P);
   vav = block_sum<double>(vav, sm.dscal);
   if (tid == 0) p.vavpart[cta] = vav;
+}
+
+// Phase C (multi-GPU only): reduce this rank's partial sums to one vector w_p(0:j) and push it, together with the
+// local v^H A v, into the exchange buffer of EVERY rank (peer stores over NVLink); the caller then signals.
+template <typename T>
+__device__ void phase_c(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
+  const int tid = threadIdx.x;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int j = p.i0 + c;
+  if (j <= 0) return;
+  const int Tn = (j + TB - 1) / TB, C = strip_len(j, G, p.P);
+  const unsigned par = (unsigned)(col_seq(p, c) & 1ull);
+  // groups of 32 rows are dealt to the CTAs; AW warps split the partial-sum slots of a group (L2-latency bound),
+  // warp 0 combines and pushes the 32 values to every rank
+  const int lane = tid & 31, warp = tid >> 5;
+  const int ngroups = (j + 31) / 32;
+  for (int g = cta; g < ngroups; g += G) {
+    const int r = g * 32 + lane;
+    const bool rv = r < j;
+    const int I = (g * 32) / TB;
+    int J0 = I + 1;
+    J0 += ((p.rank - J0) % p.P + p.P) % p.P;               // first owned tile column >= I+1
+    const int nd = J0 < Tn ? (Tn - J0 + p.P - 1) / p.P : 0;  // direct slots J0, J0+P, ...
+    const int nt = (I % p.P == p.rank) ? I / C + 1 : 0;      // band slots of an owned tile column
+    if (warp < AW) {
+      T sacc = zero_<T>();
+      if (rv) {
+        for (int q = warp; q < nd + nt; q += AW) {
+          const T* src = (q < nd) ? (p.Pd + (int64_t)(J0 + q * p.P) * p.ldp) : (p.Pt + (int64_t)(q - nd) * p.ldp);
+          sacc = add_(sacc, ldcg_(src + r));
+        }
+      }
+      sm.u.a.ared[warp * 32 + lane] = sacc;
+    }
+    __syncthreads();
+    if (warp == 0 && rv) {
+      T tot = zero_<T>();
+#pragma unroll
+      for (int w = 0; w < AW; ++w) tot = add_(tot, sm.u.a.ared[w * 32 + lane]);
+      for (int q = 0; q < p.P; ++q) ex_slot(p, q, p.rank, par)[r] = tot;
+    }
+    __syncthreads();
+  }
+  if (cta == 0) {
+    double vv = 0.0;
+    for (int g = tid; g < G; g += NT) { if (tid < NT) vv += __ldcg(p.vavpart + g); }
+    vv = block_sum<double>(vv, sm.dscal);
+    if (tid < p.P) ex_slot(p, tid, p.rank, par)[p.wstride - 1] = from_real<T>(vv);
+  }
 }
 
 template <typename T>
@@ -695,6 +808,15 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
     stamp(c, 3);
     target += gridDim.x;
     grid_barrier(p.barrier, target, p.status);
+    if (p.P > 1 && p.i0 + c > 0) {
+      phase_c<T>(p, c, sm);
+      target += gridDim.x;
+      grid_barrier(p.barrier, target, p.status, true);     // system-scope fences: peer stores are complete
+      if (blockIdx.x == 0 && threadIdx.x < p.P) {
+        __threadfence_system();
+        st_release_sys(p.peer_flag[threadIdx.x] + p.rank, col_seq(p, c));
+      }
+    }
     stamp(c, 4);
   }
 }
@@ -788,6 +910,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   int64_t ldp;
   size_t pe = partial_elems<T>(n, ldp);
   size_t bytes = (2 * pe + (size_t)n * nb + (size_t)n + 256 + (size_t)MAXZU * 2 * NBMAX + 64) * sizeof(T) +
+                 ((size_t)(n / TB + 2) * (size_t)(n / TB + 2) / 2 + 2 * (size_t)(n / TB + 2) + 16) * sizeof(GemmParams<T>) +
                  (size_t)(2 * grid + 64) * sizeof(double) + 4096 + 16 * 256;
   void* scr = ctx_scratch(bytes);
   if (!scr) return -1;
@@ -807,12 +930,58 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   p.vec_ok = vec_ok;
   p.use_tma = use_tma;
   p.trace = nullptr;
+  MgConfig& M = mg();
+  p.rank = 0; p.P = 1;
+  GemmParams<T>* GP = nullptr;
+  if (M.P > 1) {
+    if (!opts().trd_coop) { set_last_error("hetrd: multi-GPU needs the cooperative panel kernel"); return -1; }
+    if (nb != TB) { set_last_error("hetrd: multi-GPU needs trd_nb == 64 (panels aligned to the tile columns)"); return -1; }
+    p.rank = M.rank; p.P = M.P;
+    p.wstride = M.wbuf_bytes / ((int64_t)M.P * 2 * (int64_t)sizeof(T));
+    if (p.wstride < (int64_t)n + 2) { set_last_error("hetrd: multi-GPU exchange buffer too small"); return -1; }
+    for (int q = 0; q < M.P; ++q) { p.peer_w[q] = (T*)M.wbuf[q]; p.peer_flag[q] = M.flags[q]; }
+    // parameter blocks of the per-tile-column rank-2k updates of ALL panels: built once, uploaded once (no host
+    // synchronisation inside the panel loop)
+    const size_t ntc = (size_t)(n / TB + 2);
+    GP = ar.take<GemmParams<T>>(ntc * ntc / 2 / M.P + 2 * ntc + 8);
+    if (!GP) { set_last_error("hetrd: scratch arena too small (multi-GPU)"); return -1; }
+  }
   if (opts().trd_trace) {
     if (cudaMalloc(&p.trace, (size_t)n * 5 * sizeof(unsigned long long)) != cudaSuccess) p.trace = nullptr;
     else cudaMemsetAsync(p.trace, 0, (size_t)n * 5 * sizeof(unsigned long long), s);
   }
   EIGB_CUDA_CHECK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
   const bool coop = opts().trd_coop != 0;
+  std::vector<GemmParams<T>> hp_all;          // multi-GPU: rank-2k parameter blocks, panel after panel
+  std::vector<int> hp_off;
+  if (M.P > 1) {
+    int hi2 = n;
+    while (hi2 > 0) {
+      int nbp2 = hi2 < nb ? hi2 : nb;
+      if (hi2 > nb && (hi2 % nb) != 0) nbp2 = hi2 % nb;
+      const int i02 = hi2 - nbp2;
+      hp_off.push_back((int)hp_all.size());
+      const T* V = A + (int64_t)i02 * lda;
+      for (int J = M.rank; J < i02 / TB; J += M.P) {
+        GemmParams<T> q;
+        memset(&q, 0, sizeof(q));
+        q.M = (J + 1) * TB; q.N = TB; q.nseg = 2;
+        q.A[0] = V; q.lda[0] = lda; q.B[0] = p.W + J * TB; q.ldb[0] = p.ldw; q.K[0] = nbp2;
+        q.A[1] = p.W; q.lda[1] = p.ldw; q.B[1] = V + J * TB; q.ldb[1] = lda; q.K[1] = nbp2;
+        q.sa[0] = q.sa[1] = 1.0; q.sb[0] = q.sb[1] = -1.0;
+        q.C = A + (int64_t)J * TB * lda; q.ldc = lda;
+        q.alpha = -1.0; q.beta = 1.0; q.mode = 1; q.real_diag = 1; q.colmap = nullptr; q.diag_off = J * TB;
+        hp_all.push_back(q);
+      }
+      hi2 = i02;
+    }
+    hp_off.push_back((int)hp_all.size());
+    if (!hp_all.empty()) {
+      EIGB_CUDA_CHECK(cudaMemcpyAsync(GP, hp_all.data(), sizeof(GemmParams<T>) * hp_all.size(), cudaMemcpyHostToDevice, s));
+      EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+  }
+  int panel_idx = 0;
 
   int hi = n;                         // columns [0, hi) still to reduce
   while (hi > 0) {
@@ -820,6 +989,18 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     // the first (rightmost) panel absorbs the remainder so that the others are aligned to nb
     if (hi > nb && (hi % nb) != 0) nbp = hi % nb;
     p.i0 = hi - nbp; p.nbp = nbp;
+    if (M.P > 1 && p.P > 1 && hi <= opts().mg_switch_n) {
+      // small trailing matrix: the per-column exchange costs more than the tiles it saves.  Make the leading hi
+      // columns current everywhere (owner = -1: "gather all tile columns") and finish replicated (deterministic).
+      if (M.hook) M.hook(hi, 0, -1);
+      p.P = 1; p.rank = 0;
+    }
+    if (p.P > 1) {
+      p.seq_base = M.seq;
+      M.seq += (unsigned long long)nbp;
+      // the panel's columns are current only on the rank that owns this tile column: broadcast them
+      if (M.hook) M.hook(p.i0, nbp, (p.i0 / TB) % M.P);
+    }
     prof_begin(PROF_PANEL, s);
     if (coop) {
       EIGB_CUDA_CHECK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), s));
@@ -837,11 +1018,20 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     }
     prof_end(PROF_PANEL, s);
     // trailing update A(0:i0, 0:i0) -= V W^H + W V^H   (zhetrd_gpu.F90:67 / dsytrd_gpu.F90:66)
-    if (p.i0 > 0) {
+    if (p.i0 > 0 && p.P == 1) {
       ProfScope ps(PROF_HER2K, s);
       if (her2k_upper<T>(s, 'N', p.i0, nbp, -1.0, A + (int64_t)p.i0 * lda, lda, p.W, p.ldw, 1.0, A, lda) != 0)
         return -1;
+    } else if (p.i0 > 0) {
+      // multi-GPU: only the tile columns J = rank (mod P) of the trailing matrix are kept current on this rank
+      ProfScope ps(PROF_HER2K, s);
+      const int cnt = hp_off[panel_idx + 1] - hp_off[panel_idx];
+      if (cnt > 0) {
+        GemmParams<T> dummy{};
+        if (gemm_launch<T>(s, false, false, dummy, GP + hp_off[panel_idx], cnt, p.i0, TB) != 0) return -1;
+      }
     }
+    ++panel_idx;
     hi = p.i0;
   }
   int st = 0;

@@ -43,6 +43,25 @@ class CudaStages:
     def hetrd(self, a):
         return self.S.hetrd(a)
 
+    def hetrd_dist(self, a, group=None):
+        """tridiagonalization with the trailing matrix distributed over the ranks (identical outputs on all ranks)"""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # the in-kernel exchange costs ~25 us per column: it pays only when the per-column tile work is large
+        if world == 1 or a.shape[0] < self.dist_hetrd_min_n(world):
+            if getattr(self, "_ex", None) is not None:
+                self._ex.close(); self._ex = None; self._ex_key = None
+            return self.S.hetrd(a)
+        key = (a.shape[0], a.dtype)
+        if getattr(self, "_ex_key", None) != key:
+            self._ex = HetrdExchange(a.shape[0], a.dtype == torch.complex128, group)
+            self._ex_key = key
+        self._ex.bind(a)
+        return self.S.hetrd(a)
+
+    @staticmethod
+    def dist_hetrd_min_n(world):
+        return 12288 if world <= 2 else 6144
+
     def stedc(self, d, e):
         return self.S.stedc(d, e)
 
@@ -59,6 +78,64 @@ class CudaStages:
             idx = torch.arange(n, device=a.device)
             full[idx, idx] = full[idx, idx].real.to(full.dtype)
         return full.contiguous()
+
+
+class HetrdExchange:
+    """Peer-memory plumbing of the distributed tridiagonalization: every rank allocates an exchange buffer
+    [world][2][n+64] and a flag array, exports them through CUDA IPC, maps the peers' buffers and hands all
+    pointers to the library; the panel kernel then pushes its partial `w` to every peer with plain stores over
+    NVLink and spins on the flags (no host round trip per column).  The once-per-panel broadcast of the panel's
+    columns goes through the caller's communicator (NCCL via torch.distributed)."""
+
+    def __init__(self, n, cplx, group=None):
+        import ctypes as C
+        from ._lib import check, load
+        self.C = C
+        self.lib = load()
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        es = 16 if cplx else 8
+        self.wbytes = self.world * 2 * (n + 64) * es
+        fbytes = 4096
+        wptr, fptr = C.c_void_p(), C.c_void_p()
+        wh, fh = C.create_string_buffer(64), C.create_string_buffer(64)
+        check(self.lib.eigb200_mg_alloc(self.wbytes, C.byref(wptr), wh), "mg_alloc")
+        check(self.lib.eigb200_mg_alloc(fbytes, C.byref(fptr), fh), "mg_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (wh.raw, fh.raw), group=group)
+        wl, fl = (C.c_void_p * self.world)(), (C.c_void_p * self.world)()
+        for q, (hw, hf) in enumerate(handles):
+            if q == self.rank:
+                wl[q], fl[q] = wptr.value, fptr.value
+            else:
+                pw, pf = C.c_void_p(), C.c_void_p()
+                check(self.lib.eigb200_mg_open(hw, C.byref(pw)), "mg_open")
+                check(self.lib.eigb200_mg_open(hf, C.byref(pf)), "mg_open")
+                wl[q], fl[q] = pw.value, pf.value
+        self.a = None
+        HOOK = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_int)
+        self._hook = HOOK(self._panel_hook)          # keep a reference: ctypes callbacks must outlive their use
+        self._wl, self._fl = wl, fl
+        check(self.lib.eigb200_mg_config(self.rank, self.world, wl, fl, self.wbytes,
+                                         C.cast(self._hook, C.c_void_p)), "mg_config")
+        dist.barrier(group=group)
+
+    def _src(self, owner):
+        return dist.get_global_rank(self.group, owner) if self.group is not None else owner
+
+    def _panel_hook(self, i0, nbp, owner):
+        if owner >= 0:          # the panel's columns are current on their owner only
+            dist.broadcast(self.a[i0:i0 + nbp], src=self._src(owner), group=self.group)
+        else:                   # owner == -1: gather ALL 64-wide tile columns of the leading i0 columns
+            for c0 in range(0, i0, 64):
+                dist.broadcast(self.a[c0:min(c0 + 64, i0)], src=self._src((c0 // 64) % self.world), group=self.group)
+
+    def bind(self, a):
+        self.a = a
+
+    def close(self):
+        self.lib.eigb200_mg_config(0, 1, None, None, 0, None)
 
 
 def _exchange_columns(x, ranges, group):
@@ -98,7 +175,7 @@ def hegvdx_distributed(a, b, il, iu, backend=None, group=None, gather_z=True):
     _exchange_columns(yh, rng, group)
     a.copy_(yh)                      # = C^H = C (full Hermitian, both triangles)
     # 3. tridiagonalization + divide & conquer, replicated (deterministic)
-    d, e, tau = be.hetrd(a)
+    d, e, tau = be.hetrd_dist(a, group) if hasattr(be, "hetrd_dist") else be.hetrd(a)
     w, q = be.stedc(d, e)
     # 4. back-transformation and final triangular solve on this rank's eigenvector columns
     z = torch.zeros((m, n), dtype=a.dtype, device=a.device)

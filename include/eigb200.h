@@ -34,6 +34,16 @@ int64_t eigb200_scratch_bytes(int n, int is_complex);
 int eigb200_set_option(const char* name, int value);
 int eigb200_get_option(const char* name);
 
+/* ---- multi-GPU (one process per GPU): 1-D block-cyclic distribution of the trailing matrix inside ?sytrd/?hetrd ----
+ * mg_alloc: cudaMalloc + zero `bytes` and export a 64-byte CUDA IPC handle; mg_open: map a peer's allocation;
+ * mg_config: rank/world (world <= 8), the exchange buffers and flag arrays of ALL ranks (own entries = local pointers),
+ * the size of one exchange buffer (>= world*2*(n+2) elements) and a callback `void hook(int i0, int nbp, int owner)` that
+ * must broadcast columns [i0, i0+nbp) of A from rank `owner` to all ranks on the library's stream (the caller owns the
+ * communicator, e.g. NCCL through torch.distributed).  world == 1 switches the mode off. */
+int eigb200_mg_alloc(long long bytes, void** dptr, char* handle64);
+int eigb200_mg_open(const char* handle64, void** dptr);
+int eigb200_mg_config(int rank, int world, void** wbufs, void** flags, long long wbuf_bytes, void* panel_hook);
+
 /* optional profiling: CUDA-event timing per stage category and a count of the kernels this library launched.
  * categories (index into ms[8], cnt[8]): 0 potrf, 1 hegst, 2 hetrd panel kernel, 3 hetrd rank-2k update,
  * 4 stedc, 5 back-transformation, 6 final trsm, 7 other.  collect() synchronises the device. */
