@@ -131,8 +131,10 @@ def workload_config(args):
             "inputs": "family R (reference recipe A=T*T^H, B=T*T^H), seed 1234 (same problem on every rank)",
             "l2": "inputs (N^2*16 B each) larger than the 126 MB L2; A,B restored from pristine device copies "
                   "inside the timed region (2 D2D copies per step)",
-            "parallelism": ("1 problem over %d GPUs: potrf/hetrd/stedc replicated (bitwise deterministic), hegst solves, "
-                            "back-transform and final trsm split by columns + NCCL exchanges" % args.gpus)
+            "parallelism": ("1 problem over %d GPUs: hegst solves, back-transform and final trsm split by columns (NCCL "
+                            "exchanges); hetrd trailing matrix 1-D block-cyclic with in-kernel NVLink exchange when "
+                            "N >= multi_gpu.CudaStages.dist_hetrd_min_n(world), else replicated; potrf/stedc replicated "
+                            "(bitwise deterministic)" % args.gpus)
             if args.gpus > 1 else "single"}
 
 

@@ -39,6 +39,7 @@ constexpr int NBMAX = 128;    // max panel width
 constexpr int MAXZU = 64;     // max number of row chunks for the V^H v / W^H v partial dots
 constexpr int ZROWS = 512;    // rows per chunk of those dots (doubled while more than MAXZU chunks)
 constexpr int AW = 8;         // warps that split the per-row work in phase A
+constexpr int MAXBANDS = 256; // max number of strip bands (tile rows / strip length), enforced by strip_len()
 
 // Ring of tile stages filled by cp.async.bulk (TMA).  One stage = a 64x64 tile stored with a padded column
 // stride (conflict-free 128-bit reads when a warp walks 32 columns) + the x slices of the tile's rows and columns.
@@ -90,6 +91,7 @@ template <typename T>
 struct EngineSmem {
   T yt[NW][TB];        // strip end: transposed partial sums of the 16 row-group warps
   T ydiag[TB];         // D units: product of the diagonal tile with x_J (both triangles)
+  int bstart[MAXBANDS + 2];   // multi-GPU: prefix counts of the F units per band (TileIter)
 };
 template <typename T>
 struct PhaseASmem {
@@ -175,6 +177,7 @@ __host__ __device__ __forceinline__ int strip_len(int n, int G, int P = 1) {
   int c = (Tn * (Tn - 1) / 2) / (6 * G * P);
   if (c < 1) c = 1;
   if (c > 8) c = 8;
+  while ((Tn - 1) / c > MAXBANDS) ++c;
   return c;
 }
 
@@ -218,7 +221,8 @@ __device__ __forceinline__ void larfg_scalars(double2 alpha, double xnorm2, doub
 // conflict-free shared-memory loads (or from global memory with 128-bit loads when the ring is off).
 // =====================================================================================================
 struct TileIter {
-  int unit, G, NF, total, Tn, C, rank, P, TnO;
+  int unit, G, NF, total, Tn, C, rank, P, TnO, KB;
+  const int* bstart;    // P > 1: bstart[k] = number of F units in bands < k (shared memory, KB+1 entries)
   int J, I1, cur, band;
   bool has_diag, done;
   // owned tile columns are J = rank + P*jj, jj = 0..TnO-1
@@ -226,29 +230,42 @@ struct TileIter {
     const int d = Jmin - rank;
     return d <= 0 ? 0 : (d + P - 1) / P;
   }
+  __device__ __forceinline__ int band_count(int k) const {                // F units of band k
+    const int jj0 = first_owned_at_least((k + 1) * C);
+    return TnO - jj0 > 0 ? TnO - jj0 : 0;
+  }
+  // P == 1: F units before band k = k*Tn - C*k*(k+1)/2
+  __device__ __forceinline__ int prefix1(int k) const { return k * Tn - C * (k * (k + 1) / 2); }
   __device__ __forceinline__ void load_unit() {
     if (unit >= total) { done = true; return; }
     if (unit < NF) {
-      int u = unit, k = 0;
-      while (true) {
-        const int jj0 = first_owned_at_least((k + 1) * C);
-        const int cnt = TnO - jj0 > 0 ? TnO - jj0 : 0;
-        if (u < cnt) { J = rank + P * (jj0 + u); break; }
-        u -= cnt; ++k;
+      int k;
+      if (P == 1) {
+        const double bq = (double)Tn - 0.5 * (double)C;
+        k = (int)((bq - sqrt(fmax(bq * bq - 2.0 * (double)C * (double)unit, 0.0))) / (double)C);
+        if (k < 0) k = 0;
+        if (k > KB - 1) k = KB - 1;
+        while (k > 0 && prefix1(k) > unit) --k;
+        while (k + 1 < KB && prefix1(k + 1) <= unit) ++k;
+        J = (k + 1) * C + (unit - prefix1(k));
+      } else {
+        int lo = 0, hi = KB - 1;                 // largest k with bstart[k] <= unit
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (bstart[mid] <= unit) lo = mid; else hi = mid - 1; }
+        k = lo;
+        J = rank + P * (first_owned_at_least((k + 1) * C) + (unit - bstart[k]));
       }
       band = k; cur = k * C; I1 = k * C + C; has_diag = false;
     } else {
       J = rank + P * (unit - NF); band = J / C; cur = band * C; I1 = J; has_diag = true;
     }
   }
-  __device__ __forceinline__ void init(int cta, int G_, int Tn_, int C_, int rank_ = 0, int P_ = 1) {
-    G = G_; Tn = Tn_; C = C_; rank = rank_; P = P_; done = false;
+  // number of bands that have F units at all: (k+1)*C < Tn
+  __device__ __forceinline__ static int num_bands(int Tn_, int C_) { return Tn_ > 0 ? (Tn_ - 1) / C_ : 0; }
+  __device__ __forceinline__ void init(int cta, int G_, int Tn_, int C_, int rank_, int P_, const int* bstart_) {
+    G = G_; Tn = Tn_; C = C_; rank = rank_; P = P_; done = false; bstart = bstart_;
     TnO = rank < Tn ? (Tn - rank + P - 1) / P : 0;
-    NF = 0;
-    for (int k = 0; (k + 1) * C < Tn; ++k) {
-      const int jj0 = first_owned_at_least((k + 1) * C);
-      NF += TnO - jj0 > 0 ? TnO - jj0 : 0;
-    }
+    KB = num_bands(Tn, C);
+    NF = (P == 1) ? prefix1(KB) : (KB > 0 ? bstart[KB] : 0);
     total = NF + TnO;
     unit = cta;
     load_unit();
@@ -328,8 +345,18 @@ __device__ double tile_engine(const T* __restrict__ A, int64_t lda, int n, const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Tn = (n + TB - 1) / TB;
   double vav = 0.0;
+  if (P > 1) {
+    // per-band unit counts depend on the ownership pattern: tabulate their prefix sums once per call
+    const int KB = TileIter::num_bands(Tn, C);
+    TileIter tmp; tmp.Tn = Tn; tmp.C = C; tmp.rank = rank; tmp.P = P;
+    tmp.TnO = rank < Tn ? (Tn - rank + P - 1) / P : 0;
+    for (int k = tid; k < KB; k += blockDim.x) es.bstart[k + 1] = tmp.band_count(k);
+    __syncthreads();
+    if (tid == 0) { int acc = 0; es.bstart[0] = 0; for (int k = 1; k <= KB; ++k) { acc += es.bstart[k]; es.bstart[k] = acc; } }
+    __syncthreads();
+  }
   TileIter it;
-  it.init(cta, G, Tn, C, rank, P);
+  it.init(cta, G, Tn, C, rank, P, es.bstart);
   int I, J, band; bool diag, first, last;
 
   if (warp >= NW) {
@@ -511,7 +538,7 @@ __global__ void pad_copy_kernel(const T* x, int n, T* xpad, int npad) {
 // =====================================================================================================
 // Panel phases
 // =====================================================================================================
-template <typename T>
+template <typename T, bool MG>
 __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -520,10 +547,11 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
   const int jp = j + 1;                         // order of the product done for column c+1
   const bool have_prev = (c + 1 <= nbp - 1) && (jp >= 1) && !(c == -1 && p.i0 == 0);
   const int cprev = c + 1;
-  const int Cp = strip_len(jp, G, p.P);         // strip length used by the previous phase B
+  const int Pn = MG ? p.P : 1;                  // compile-time 1 in the single-GPU kernel
+  const int Cp = strip_len(jp, G, Pn);          // strip length used by the previous phase B
   T tau_p = zero_<T>();
   double alpha_p = 0.0;
-  const bool mg = p.P > 1;
+  const bool mg = MG && p.P > 1;
   const unsigned long long seqp = have_prev ? col_seq(p, cprev) : 0ull;
   const unsigned parp = (unsigned)(seqp & 1ull);
   if (mg && have_prev) {
@@ -676,7 +704,7 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
   }
 }
 
-template <typename T>
+template <typename T, bool MG>
 __device__ void phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingState& rs, const CUtensorMap* tmap) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -704,29 +732,46 @@ __device__ void phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, Ring
   auto xval = [&](int r) -> T { return xfix(r, r < j ? p.xbuf[r] : zero_<T>()); };
   // -- partial dots z1 = V^H v, z2 = W^H v: unit = (row chunk u, group of NW (which, cc) pairs), one pair per warp
   const int nf = p.nbp - 1 - c;      // finished columns cc in (c, nbp)
-  if (nf > 0 && warp < NW) {
+  if (nf > 0) {
     const int zch = zchunk_rows(j);
     const int nzch = (j + zch - 1) / zch;
     const int ngrp = (2 * nf + NW - 1) / NW;
+    T* xs = sm.u.a.ared;               // 512-row slice of v staged in shared memory (phase-A scratch is free here)
     // start at the far end of the CTA range so that these units do not pile onto the CTAs with the longest strips
     for (int unit = (G - 1 - cta); unit < nzch * ngrp; unit += G) {
       const int u = unit / ngrp, grp = unit % ngrp;
       const int q = grp * NW + warp;
-      if (q < 2 * nf) {
-        const int rbeg = u * zch, rend = min(j, rbeg + zch);
-        const int which = q / nf, cc = c + 1 + (q % nf);
-        const T* col = which ? (p.W + (int64_t)cc * p.ldw) : (p.A + (int64_t)(p.i0 + cc) * p.lda);
-        T s = zero_<T>();
-        for (int r = rbeg + lane; r < rend; r += 32) fmac_(s, ldcg_(col + r), xval(r));
-        s = warp_sum(s);
-        if (lane == 0) p.zpart[((int64_t)u * 2 + which) * NBMAX + cc] = s;
+      const bool active = warp < NW && q < 2 * nf;
+      const int which = active ? q / nf : 0, cc = active ? c + 1 + (q % nf) : 0;
+      const T* col = which ? (p.W + (int64_t)cc * p.ldw) : (p.A + (int64_t)(p.i0 + cc) * p.lda);
+      T sacc = zero_<T>();
+      for (int r0 = u * zch; r0 < min(j, (u + 1) * zch); r0 += ZROWS) {
+        const int rows = min(ZROWS, min(j, (u + 1) * zch) - r0);
+        __syncthreads();
+        for (int i = tid; i < rows; i += blockDim.x) xs[i] = xval(r0 + i);
+        __syncthreads();
+        if (active) {
+          // 512 rows = 16 loads per lane, issued 8 at a time (this loop is L2-latency bound)
+          for (int i0 = lane; i0 < rows; i0 += 256) {
+            T cv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = i0 + 32 * k; cv[k] = i < rows ? ldcg_(col + r0 + i) : zero_<T>(); }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = i0 + 32 * k; if (i < rows) fmac_(sacc, cv[k], xs[i]); }
+          }
+        }
+      }
+      if (active) {
+        sacc = warp_sum(sacc);
+        if (lane == 0) p.zpart[((int64_t)u * 2 + which) * NBMAX + cc] = sacc;
       }
     }
   }
   // -- the tile engine: w_raw partials and v^H A v
   __syncthreads();     // phase-A scratch is dead from here on: the engine overlays it
-  double vav = tile_engine<T>(p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, cta, G, strip_len(j, G, p.P),
-                              p.use_tma != 0, p.vec_ok, ring, sm.full, sm.empty, rs, sm.u.e, tmap, p.rank, p.P);
+  const int Pn = MG ? p.P : 1, rk = MG ? p.rank : 0;
+  double vav = tile_engine<T>(p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, cta, G, strip_len(j, G, Pn),
+                              p.use_tma != 0, p.vec_ok, ring, sm.full, sm.empty, rs, sm.u.e, tmap, rk, Pn);
   vav = block_sum<double>(vav, sm.dscal);
   if (tid == 0) p.vavpart[cta] = vav;
 }
@@ -780,7 +825,7 @@ __device__ void phase_c(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
   }
 }
 
-template <typename T>
+template <typename T, bool MG>
 __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constant__ CUtensorMap tmap, TrdP<T> p) {
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ PanelSmem<T> sm;
@@ -798,17 +843,17 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
   };
   for (int c = p.nbp - 1; c >= -1; --c) {
     if (c >= 0) stamp(c, 0);
-    phase_a<T>(p, c, sm);
+    phase_a<T, MG>(p, c, sm);
     if (c < 0) break;
     stamp(c, 1);
     target += gridDim.x;
     grid_barrier(p.barrier, target, p.status);
     stamp(c, 2);
-    phase_b<T>(p, c, sm, ring, rs, &tmap);
+    phase_b<T, MG>(p, c, sm, ring, rs, &tmap);
     stamp(c, 3);
     target += gridDim.x;
     grid_barrier(p.barrier, target, p.status);
-    if (p.P > 1 && p.i0 + c > 0) {
+    if (MG && p.P > 1 && p.i0 + c > 0) {
       phase_c<T>(p, c, sm);
       target += gridDim.x;
       grid_barrier(p.barrier, target, p.status, true);     // system-scope fences: peer stores are complete
@@ -823,7 +868,7 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
 template <typename T>
 __global__ void __launch_bounds__(NTT, 1) phase_a_kernel(TrdP<T> p, int c) {
   __shared__ PanelSmem<T> sm;
-  phase_a<T>(p, c, sm);
+  phase_a<T, false>(p, c, sm);
 }
 template <typename T>
 __global__ void __launch_bounds__(NTT, 1) phase_b_kernel(const __grid_constant__ CUtensorMap tmap, TrdP<T> p, int c) {
@@ -832,20 +877,21 @@ __global__ void __launch_bounds__(NTT, 1) phase_b_kernel(const __grid_constant__
   T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
   RingState rs; rs.stage = 0; rs.par = (threadIdx.x >= NT) ? 0xffffffffu : 0u;
   if (p.use_tma) ring_init<T>(ring, sm.full, sm.empty, rs);
-  phase_b<T>(p, c, sm, ring, rs, &tmap);
+  phase_b<T, false>(p, c, sm, ring, rs, &tmap);
 }
 
 template <typename T>
 int panel_grid(int& grid, size_t dyn_smem) {
   static bool attr_set = false;
   if (!attr_set) {
-    EIGB_CUDA_CHECK(cudaFuncSetAttribute(panel_coop_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
+    EIGB_CUDA_CHECK(cudaFuncSetAttribute(panel_coop_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
+    EIGB_CUDA_CHECK(cudaFuncSetAttribute(panel_coop_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
     EIGB_CUDA_CHECK(cudaFuncSetAttribute(phase_b_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
     EIGB_CUDA_CHECK(cudaFuncSetAttribute(hemv_tiles_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
     attr_set = true;
   }
   int per_sm = 0;
-  EIGB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_coop_kernel<T>, NTT, dyn_smem));
+  EIGB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_coop_kernel<T, true>, NTT, dyn_smem));
   if (per_sm < 1) { set_last_error("panel kernel does not fit on an SM"); return -1; }
   grid = ctx().num_sms;      // one persistent CTA per SM
   return 0;
@@ -1005,7 +1051,8 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     if (coop) {
       EIGB_CUDA_CHECK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), s));
       void* args[] = {&tmap, &p};
-      EIGB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)panel_coop_kernel<T>, dim3(grid), dim3(NTT), args, dyn, s));
+      void* kfn = (p.P > 1) ? (void*)panel_coop_kernel<T, true> : (void*)panel_coop_kernel<T, false>;
+      EIGB_CUDA_CHECK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(NTT), args, dyn, s));
       count_launch(1);
     } else {
       for (int cc = nbp - 1; cc >= -1; --cc) {
