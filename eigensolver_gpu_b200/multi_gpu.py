@@ -3,10 +3,12 @@
 Round-1 partition: every stage whose right-hand sides are independent is split 1-D by
 columns across the ranks -- the two triangular solves of the reduction to standard form (`U^-H A`, then
 `U^-H Y^H` using C = C^H), the back-transformation `Z <- Q Z` and the final `Z <- U^-1 Z` -- each followed by
-one exchange of the column blocks.  The Cholesky factorization, the tridiagonalization and the tridiagonal
-divide & conquer run replicated; they are bitwise deterministic (no atomics), so all ranks hold identical
-`U`, reflectors and tridiagonal eigenvectors without any broadcast.  The 1-D block-column distribution of
-the trailing matrix inside the tridiagonalization (per-column all-reduce of `w`) is the next step.
+one exchange of the column blocks.  The tridiagonalization distributes the trailing matrix 1-D block-cyclically by 64-wide tile columns
+(`HetrdExchange`: each rank streams only its tiles, the partial `w` vectors are exchanged INSIDE the persistent
+panel kernel through CUDA-IPC peer buffers over NVLink with flag signalling -- no host round trip per column;
+once per panel the panel's columns are broadcast with NCCL).  The Cholesky factorization and the tridiagonal
+divide & conquer run replicated; everything is bitwise deterministic (no atomics, fixed summation order
+across ranks), so all ranks hold identical `U`, reflectors and tridiagonal eigenvectors.
 
 The orchestration is written against a small "stage backend" so that the partition / exchange logic is
 exercised on CPU with the gloo backend (tests/test_multi_gpu_cpu.py) while the product uses the CUDA stages.
@@ -60,7 +62,7 @@ class CudaStages:
 
     @staticmethod
     def dist_hetrd_min_n(world):
-        return 12288 if world <= 2 else 6144
+        return 6144 if world <= 2 else 4096
 
     def stedc(self, d, e):
         return self.S.stedc(d, e)
