@@ -36,13 +36,11 @@ constexpr int NW = NT / 32;
 constexpr int NTT = NT + 32;  // + one TMA producer warp
 constexpr int NWT = NTT / 32;
 constexpr int NBMAX = 128;    // max panel width
-constexpr int MAXZU = 64;     // max number of row chunks for the V^H v / W^H v partial dots
-constexpr int ZROWS = 512;    // rows per chunk of those dots (doubled while more than MAXZU chunks)
-constexpr int AW = 8;         // warps that split the per-row work in phase A
+constexpr int AW = 8;         // warps that split the per-row work in phase C (multi-GPU)
+constexpr int TRSLOTS = 16;    // globaltimer stamps per column when tracing
 constexpr int MAXBANDS = 256; // max number of strip bands (tile rows / strip length), enforced by strip_len()
 
-// Ring of tile stages filled by cp.async.bulk (TMA).  One stage = a 64x64 tile stored with a padded column
-// stride (conflict-free 128-bit reads when a warp walks 32 columns) + the x slices of the tile's rows and columns.
+// Ring of tile stages filled by TMA.  One stage = a 64x64 tile + the x slices of the tile's rows and columns.
 // A tile arrives as NBOX boxes of 16 doubles x 64 columns (8 KB each, one cp.async.bulk.tensor.2d per box) in the
 // 128-byte swizzled layout, which makes the "one lane per tile column" reads bank-conflict free.
 template <typename T> struct RingCfg;
@@ -62,15 +60,16 @@ struct TrdP {
   double* d; double* e; T* tau;
   T* xbuf;                     // unscaled updated column
   T* Pd; T* Pt; int64_t ldp;   // partials: Pd[J*ldp + r] (direct, from tile (I(r),J), J > I), Pt[k*ldp + r] (band k)
-  T* zpart;                    // [MAXZU][2][NBMAX]
+  T* zfin;                     // [2][NBMAX]: z1 = V^H v, z2 = W^H v of the latest reflector
   double* npart;               // [G] partial sums of squares
-  double* vavpart;             // [G] partial v^H A v
+  double* vavunit;             // [units] partial v^H A v, one slot per tile unit (deterministic whatever CTA ran it)
   T* alpha_slot;               // a(j-1, j) before scaling
+  T* scale_slot;               // 1 / (alpha - beta) of the latest reflector
   unsigned* barrier;
+  unsigned* qctr;              // [NBMAX] tile-unit queue heads, one per panel column (zeroed per panel)
   int* status;
-  int vec_ok;                  // 16-byte loads allowed (real: A 16B aligned and lda even)
-  int use_tma;                 // off-diagonal tiles staged through the TMA ring (needs vec_ok)
-  unsigned long long* trace;   // optional: 5 globaltimer stamps per column (CTA 0), profiling aid
+  int use_tma;                 // tiles staged through the TMA ring (needs 16-byte aligned columns)
+  unsigned long long* trace;   // optional: TRSLOTS globaltimer stamps per column (CTA 0), profiling aid
   // multi-GPU (1-D block-cyclic distribution of the 64-wide tile columns of the trailing matrix over P ranks)
   int rank, P;                 // P == 1: single GPU
   T* peer_w[8];                // peer_w[q] = rank q's exchange buffer [P][2][wstride] (peer-mapped, NVLink)
@@ -87,16 +86,30 @@ struct RingState {
   unsigned par;
 };
 
+// per-column descriptor, see compute_desc()
+struct ColDesc {
+  int j, Tn, C, rcpC, KB, NF, total;   // order, tile rows, strip length (+ 2^16 reciprocal), unit map (P == 1)
+  int R;                               // rows per CTA in the phase A that follows
+  int ndj, nsj;                        // partial-sum slots of the last row (direct / total)
+};
+
+// what the producer warp tells the consumers about the tile in a ring stage
+struct __align__(16) TileMeta { int I, J, unit, flags; };
+constexpr int MF_FIRST = 1, MF_LAST = 2, MF_DIAG = 4, MF_END = 8;
+
 template <typename T>
 struct EngineSmem {
-  T yt[NW][TB];        // strip end: transposed partial sums of the 16 row-group warps
+  T yt[NW][TB];        // strip end: transposed partial sums of the 16 row-group warps (also: v slice of the z-dot units)
   T ydiag[TB];         // D units: product of the diagonal tile with x_J (both triangles)
-  int bstart[MAXBANDS + 2];   // multi-GPU: prefix counts of the F units per band (TileIter)
+  double vred[NW];     // strip end: per-warp v^H A v of the unit
+  int bstart[MAXBANDS + 2];   // multi-GPU: prefix counts of the F units per band
 };
 template <typename T>
 struct PhaseASmem {
   T z1[NBMAX], z2[NBMAX], rowV[NBMAX], rowW[NBMAX];
-  T ared[AW * 32 * 3];   // per-warp slices of (t1, t2, wraw) for one group of 32 rows
+  T ared[NW * 32 * 2];   // per-warp slices of (wraw - t1, t2) for the rows in flight
+  T s_tau, s_scale, s_wj;   // scalars of the previous reflector, from the scalar warp
+  double s_alpha;
 };
 // phase A and the tile engine never run at the same time: their scratch is overlaid
 template <typename T>
@@ -108,7 +121,11 @@ struct PanelSmem {
   } u;
   T tred[NWT];
   double dscal[NWT];
+  double nred[NWT];
   uint64_t full[8], empty[8];   // ring mbarriers
+  TileMeta meta[8];
+  ColDesc cd[2];                // descriptors of the current and the next product (parity of the panel column)
+  T hh_scale;                   // phase B: 1 / (alpha - beta) from warp 0
 };
 
 __device__ __forceinline__ double ldcg_(const double* p) { return __ldcg(p); }
@@ -122,23 +139,35 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   unsigned ok = 0;
   const unsigned a = smem_u32(bar);
+  unsigned spins = 0;
   do {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();     // watchdog: a broken pipeline must fail, never hang the GPU
   } while (!ok);
 }
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+               :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" :: "n"(NT) : "memory"); }
 
 // ---- grid barrier (monotonic counter, watchdog-protected) --------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int* status, bool sys = false) {
+template <class Hook>
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int* status, bool sys, Hook hook) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    hook();                      // last per-CTA global stores of the phase (e.g. the partial norm)
     if (sys) __threadfence_system(); else __threadfence();
     atomicAdd(bar, 1u);
     unsigned long long spins = 0;
@@ -146,7 +175,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int
       unsigned v;
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(bar) : "memory");
       if (v >= target) break;
-      if (++spins > (1ull << 26)) { atomicExch(status, 77); break; }   // watchdog: never hang the GPU
+      if (++spins > (1ull << 25)) { atomicExch(status, 77); __trap(); }   // watchdog: never hang the GPU
     }
     __threadfence();
   }
@@ -154,7 +183,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int
 }
 
 template <typename T>
-__device__ __forceinline__ T block_sum(T v, T* red /* >= NW entries */) {
+__device__ __forceinline__ T block_sum(T v, T* red /* >= NWT entries */) {
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
@@ -165,12 +194,6 @@ __device__ __forceinline__ T block_sum(T v, T* red /* >= NW entries */) {
   return s;
 }
 
-__host__ __device__ __forceinline__ int zchunk_rows(int n) {
-  int ch = ZROWS;
-  while ((n + ch - 1) / ch > MAXZU) ch *= 2;
-  return ch;
-}
-
 // tiles per strip chunk for an order-n product on G CTAs: aim at >= 6 units per CTA, at most 8 tiles per unit
 __host__ __device__ __forceinline__ int strip_len(int n, int G, int P = 1) {
   const int Tn = (n + TB - 1) / TB;
@@ -179,6 +202,26 @@ __host__ __device__ __forceinline__ int strip_len(int n, int G, int P = 1) {
   if (c > 8) c = 8;
   while ((Tn - 1) / c > MAXBANDS) ++c;
   return c;
+}
+
+// Everything a CTA needs to know about the product of order j (panel column c).  It is used by phase B(c) and by
+// the phase A that follows (c-1) and is derived one column ahead by a single thread that would otherwise idle
+// (the producer warp, after its last tile): integer divisions and square roots cost ~25 dependent instructions
+// each, and 17 warps repeating them on the critical path of every column was a measurable part of it.
+__device__ void compute_desc(ColDesc& d, int j, int G, int P) {
+  d.j = j;
+  if (j <= 0) { d.Tn = 0; d.C = 1; d.rcpC = 65536; d.KB = 0; d.NF = 0; d.total = 0; d.R = 0; d.ndj = 0; d.nsj = 0; return; }
+  const int Tn = (j + TB - 1) / TB;
+  const int C = strip_len(j, G, P);
+  d.Tn = Tn; d.C = C; d.rcpC = (65536 + C - 1) / C;
+  d.KB = (Tn - 1) / C;
+  d.NF = d.KB * Tn - C * (d.KB * (d.KB + 1) / 2);
+  d.total = d.NF + Tn;                 // P == 1 (P > 1: engine_prepare tabulates the owned units)
+  int R = (j + G - 1) / G;
+  d.R = (R + 7) & ~7;
+  const int Ij = (j - 1) / TB;         // tile row of the last row (row j' = j-1 of the following phase A)
+  d.ndj = Tn - (Ij + 1);
+  d.nsj = d.ndj + Ij / C + 1;
 }
 
 // ---- Householder scalars: LAPACK ?larfg without the safmin loop (zhetrd_gpu.F90:277-331, dsytrd_gpu.F90:408-443)
@@ -215,16 +258,18 @@ __device__ __forceinline__ void larfg_scalars(double2 alpha, double xnorm2, doub
 //   outputs: Pd[J*ldp + r]  = (A_IJ x_J)(r)            for every off-diagonal tile (I, J), r in block I
 //            Pt[k*ldp + c]  = sum over the unit's tiles of (A_IJ^H x_I)(c)  (+ the full diagonal-tile product for
 //                             D units), c in block J, k = the unit's band
+//            vavunit[u]     = the unit's share of Re(x^H A x)
 //   so  y(r) = sum_{J > I(r)} Pd[J][r] + sum_{k <= floor(I(r)/C)} Pt[k][r].
-// Thread mapping (512 threads): warp w -> row group wr = w%4 (16 rows), column group wc = w/4 (16 columns);
-// a thread holds RH consecutive rows x CQ columns (real 2x4, complex 1x8), read from the ring with 128-bit
-// conflict-free shared-memory loads (or from global memory with 128-bit loads when the ring is off).
+// Every output slot is determined by the unit, not by the CTA that ran it, so the units can be handed out
+// dynamically: unit `cta` is static, the following ones come from an atomic queue head (F units first, then the
+// D units in decreasing size -- longest-processing-time order -- so that all CTAs finish within about one tile).
+// One producer warp decodes units, announces every tile through a small descriptor in shared memory and (ring
+// on) fetches it with TMA; 16 consumer warps follow the descriptors: warp w owns tile rows [4w, 4w+4), lane l owns
+// tile columns l and l+32.
 // =====================================================================================================
-struct TileIter {
-  int unit, G, NF, total, Tn, C, rank, P, TnO, KB;
+struct UnitMap {
+  int Tn, C, rcpC, rank, P, TnO, KB, NF, total;
   const int* bstart;    // P > 1: bstart[k] = number of F units in bands < k (shared memory, KB+1 entries)
-  int J, I1, cur, band;
-  bool has_diag, done;
   // owned tile columns are J = rank + P*jj, jj = 0..TnO-1
   __device__ __forceinline__ int first_owned_at_least(int Jmin) const {   // smallest jj with rank + P*jj >= Jmin
     const int d = Jmin - rank;
@@ -236,8 +281,17 @@ struct TileIter {
   }
   // P == 1: F units before band k = k*Tn - C*k*(k+1)/2
   __device__ __forceinline__ int prefix1(int k) const { return k * Tn - C * (k * (k + 1) / 2); }
-  __device__ __forceinline__ void load_unit() {
-    if (unit >= total) { done = true; return; }
+  // number of bands that have F units at all: (k+1)*C < Tn
+  __device__ __forceinline__ static int num_bands(int Tn_, int C_) { return Tn_ > 0 ? (Tn_ - 1) / C_ : 0; }
+  __device__ __forceinline__ void init(int n, int C_, int rank_, int P_, const int* bstart_) {
+    Tn = (n + TB - 1) / TB; C = C_; rcpC = (65536 + C_ - 1) / C_; rank = rank_; P = P_; bstart = bstart_;
+    TnO = rank < Tn ? (Tn - rank + P - 1) / P : 0;
+    KB = num_bands(Tn, C);
+    NF = (P == 1) ? prefix1(KB) : (KB > 0 ? bstart[KB] : 0);
+    total = NF + TnO;
+  }
+  // tiles of a unit: off-diagonal (I, J) for I in [I0, I1), then the diagonal tile (J, J) when has_diag
+  __device__ __forceinline__ void decode(int unit, int& J, int& I0, int& I1, bool& has_diag) const {
     if (unit < NF) {
       int k;
       if (P == 1) {
@@ -254,51 +308,29 @@ struct TileIter {
         k = lo;
         J = rank + P * (first_owned_at_least((k + 1) * C) + (unit - bstart[k]));
       }
-      band = k; cur = k * C; I1 = k * C + C; has_diag = false;
+      I0 = k * C; I1 = k * C + C; has_diag = false;
     } else {
-      J = rank + P * (unit - NF); band = J / C; cur = band * C; I1 = J; has_diag = true;
+      int q = unit - NF;
+      if (P == 1) {
+        // decreasing size: a D unit has (J mod C) + 1 tiles; residue classes from the largest down
+        int s = (C < Tn ? C : Tn) - 1;
+        for (; s > 0; --s) {
+          const int cnt = (Tn - 1 - s) / C + 1;
+          if (q < cnt) break;
+          q -= cnt;
+        }
+        J = s + C * q;
+      } else {
+        J = rank + P * q;
+      }
+      I0 = (J / C) * C; I1 = J; has_diag = true;
     }
-  }
-  // number of bands that have F units at all: (k+1)*C < Tn
-  __device__ __forceinline__ static int num_bands(int Tn_, int C_) { return Tn_ > 0 ? (Tn_ - 1) / C_ : 0; }
-  __device__ __forceinline__ void init(int cta, int G_, int Tn_, int C_, int rank_, int P_, const int* bstart_) {
-    G = G_; Tn = Tn_; C = C_; rank = rank_; P = P_; done = false; bstart = bstart_;
-    TnO = rank < Tn ? (Tn - rank + P - 1) / P : 0;
-    KB = num_bands(Tn, C);
-    NF = (P == 1) ? prefix1(KB) : (KB > 0 ? bstart[KB] : 0);
-    total = NF + TnO;
-    unit = cta;
-    load_unit();
-  }
-  // returns false when exhausted; otherwise the next tile of this CTA
-  __device__ __forceinline__ bool next(int& I, int& Jo, bool& diag, bool& first, bool& last, int& bnd) {
-    if (done) return false;
-    Jo = J; bnd = band;
-    const int I0 = band * C;
-    if (cur < I1) { I = cur; diag = false; first = (cur == I0); ++cur; last = (cur == I1) && !has_diag; }
-    else { I = J; diag = true; first = (I0 == I1); last = true; has_diag = false; }
-    if (last) { unit += G; load_unit(); }
-    return true;
   }
 };
 
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
-               :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" :: "n"(NT) : "memory"); }
-
-template <typename T>
-__device__ void ring_init(T* ring, uint64_t* full, uint64_t* empty, RingState& rs) {
-  constexpr int S = RingCfg<T>::STAGES;
-  // zero the ring once (tile columns beyond the matrix edge are never copied; they must not hold NaN patterns)
-  double* rz = reinterpret_cast<double*>(ring);
-  for (int i = threadIdx.x; i < (int)((ring_bytes<T>() - 1024) / sizeof(double)); i += blockDim.x) rz[i] = 0.0;
+__device__ __forceinline__ void ring_init(uint64_t* full, uint64_t* empty, int stages, RingState& rs) {
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -333,63 +365,95 @@ __device__ __forceinline__ void warp_reduce4(double2 (&v)[4], int lane) {
   v[0] = mkz(re[0], im[0]);
 }
 
-// XR: (global index r, raw x value) -> x(r) (must return 0 for r >= n); xsrc: x stored with at least
-// roundup64(n) readable entries.  Returns this thread's share of Re(x^H A x).  All NTT threads must call.
-//   consumer warp w (0..15) owns tile rows [4w, 4w+4); lane l owns tile columns l and l+32.
-template <typename T, class XR>
-__device__ double tile_engine(const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc, XR xfix, T* Pd,
-                              T* Pt, int64_t ldp, int cta, int G, int C, bool tma, int vec_ok, T* ring, uint64_t* full,
-                              uint64_t* empty, RingState& rs, EngineSmem<T>& es, const CUtensorMap* tmap, int rank = 0,
-                              int P = 1) {
-  constexpr int S = RingCfg<T>::STAGES, NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Tn = (n + TB - 1) / TB;
-  double vav = 0.0;
+// All NTT threads must call.  P > 1: tabulates the per-band unit counts of this rank's ownership pattern.
+template <typename T>
+__device__ __forceinline__ UnitMap engine_prepare(int n, int C, int rank, int P, EngineSmem<T>& es) {
   if (P > 1) {
-    // per-band unit counts depend on the ownership pattern: tabulate their prefix sums once per call
-    const int KB = TileIter::num_bands(Tn, C);
-    TileIter tmp; tmp.Tn = Tn; tmp.C = C; tmp.rank = rank; tmp.P = P;
+    const int Tn = (n + TB - 1) / TB;
+    const int KB = UnitMap::num_bands(Tn, C);
+    UnitMap tmp; tmp.Tn = Tn; tmp.C = C; tmp.rank = rank; tmp.P = P;
     tmp.TnO = rank < Tn ? (Tn - rank + P - 1) / P : 0;
-    for (int k = tid; k < KB; k += blockDim.x) es.bstart[k + 1] = tmp.band_count(k);
+    for (int k = threadIdx.x; k < KB; k += blockDim.x) es.bstart[k + 1] = tmp.band_count(k);
     __syncthreads();
-    if (tid == 0) { int acc = 0; es.bstart[0] = 0; for (int k = 1; k <= KB; ++k) { acc += es.bstart[k]; es.bstart[k] = acc; } }
+    if (threadIdx.x == 0) { int acc = 0; es.bstart[0] = 0; for (int k = 1; k <= KB; ++k) { acc += es.bstart[k]; es.bstart[k] = acc; } }
     __syncthreads();
   }
-  TileIter it;
-  it.init(cta, G, Tn, C, rank, P, es.bstart);
-  int I, J, band; bool diag, first, last;
+  UnitMap um;
+  um.init(n, C, rank, P, es.bstart);
+  return um;
+}
+
+// XR: (global index r, raw x value) -> x(r) (must return 0 for r >= n); xsrc: x stored with at least
+// roundup64(n) readable entries.  All NTT threads must call; ends with a CTA barrier.
+template <typename T, class XR>
+__device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc,
+                           XR xfix, T* Pd, T* Pt, int64_t ldp, double* vavunit, unsigned* qctr, int cta, int G, bool tma,
+                           T* ring, uint64_t* full, uint64_t* empty, TileMeta* meta, RingState& rs, EngineSmem<T>& es,
+                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc) {
+  constexpr int S = RingCfg<T>::STAGES, NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int st = rs.stage;
 
   if (warp >= NW) {
-    // ===================== TMA producer warp =====================
-    if (tma) {
-      while (it.next(I, J, diag, first, last, band)) {
-        if (diag) continue;
-        const int st = rs.stage;
+    // ===================== producer warp =====================
+    int unit = cta;                       // first unit static, the following ones from the queue
+    for (;;) {
+      const bool end = unit >= um.total;
+      int J = 0, I0 = 0, I1 = 0; bool hd = false;
+      if (!end) um.decode(unit, J, I0, I1, hd);
+      const int ntile = end ? 1 : (I1 - I0) + (hd ? 1 : 0);
+      for (int t = 0; t < ntile; ++t) {
+        const bool diag = !end && hd && (t == ntile - 1);
+        const int I = diag ? J : I0 + t;
         mbar_wait(&empty[st], (rs.par >> st) & 1u);
         rs.par ^= (1u << st);
         T* dst = ring + (size_t)st * stage_elems<T>();
-        if (lane == 0) mbar_expect_tx(&full[st], (unsigned)(stage_elems<T>() * sizeof(T)));
+        if (lane == 0) {
+          TileMeta m;
+          m.I = I; m.J = J; m.unit = unit;
+          m.flags = end ? MF_END : ((t == 0 ? MF_FIRST : 0) | (t == ntile - 1 ? MF_LAST : 0) | (diag ? MF_DIAG : 0));
+          meta[st] = m;
+          if (end || !tma) mbar_arrive(&full[st]);
+          else mbar_expect_tx(&full[st], (unsigned)(stage_elems<T>() * sizeof(T)));
+        }
         __syncwarp();
-        if (lane < NBOX)
-          tma_load_2d(reinterpret_cast<char*>(dst) + lane * BOX_BYTES, tmap, (I * TB) * DPE + lane * 16, J * TB, &full[st]);
-        else if (lane == NBOX) bulk_copy_g2s(dst + TB * TB, xsrc + I * TB, (unsigned)(TB * sizeof(T)), &full[st]);
-        else if (lane == NBOX + 1) bulk_copy_g2s(dst + TB * TB + TB, xsrc + J * TB, (unsigned)(TB * sizeof(T)), &full[st]);
-        rs.stage = (st + 1) % S;
+        if (!end && tma) {
+          if (lane < NBOX)
+            tma_load_2d(reinterpret_cast<char*>(dst) + lane * BOX_BYTES, tmap, (I * TB) * DPE + lane * 16, J * TB, &full[st]);
+          else if (lane == NBOX) bulk_copy_g2s(dst + TB * TB, xsrc + I * TB, (unsigned)(TB * sizeof(T)), &full[st]);
+          else if (lane == NBOX + 1) bulk_copy_g2s(dst + TB * TB + TB, xsrc + J * TB, (unsigned)(TB * sizeof(T)), &full[st]);
+        }
+        st = (st + 1) % S;
       }
+      if (end) break;
+      int nu = 0;
+      if (lane == 0) nu = G + (int)atomicAdd(qctr, 1u);
+      unit = __shfl_sync(0xffffffffu, nu, 0);
     }
+    // idle from here on: derive the next product's descriptor while the consumers drain the ring
+    if (lane == 0 && next_cd != nullptr) compute_desc(*next_cd, jnext, G, Pdesc);
   } else {
     // ===================== consumer warps =====================
     const int r4 = 4 * warp;
     T acct[2] = {zero_<T>(), zero_<T>()};
-    while (it.next(I, J, diag, first, last, band)) {
-      if (first) { acct[0] = zero_<T>(); acct[1] = zero_<T>(); }
+    double vav = 0.0;
+    for (;;) {
+      mbar_wait(&full[st], (rs.par >> st) & 1u);
+      rs.par ^= (1u << st);
+      const int4 mv = *reinterpret_cast<const int4*>(&meta[st]);
+      const int I = mv.x, J = mv.y, unit = mv.z, fl = mv.w;
+      const int stc = st;
+      st = (st + 1) % S;
+      if (fl & MF_END) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stc]);
+        break;
+      }
+      const bool diag = (fl & MF_DIAG) != 0;
+      if (fl & MF_FIRST) { acct[0] = zero_<T>(); acct[1] = zero_<T>(); vav = 0.0; }
       T a[4][2], xr[4], xc[2];
-      if (tma && !diag) {
-        const int st = rs.stage;
-        mbar_wait(&full[st], (rs.par >> st) & 1u);
-        rs.par ^= (1u << st);
-        rs.stage = (st + 1) % S;
-        const T* tile = ring + (size_t)st * stage_elems<T>();
+      if (tma) {
+        const T* tile = ring + (size_t)stc * stage_elems<T>();
         // this warp's 4 rows live in box (4w*DPE)/16, 16-byte chunks k0.. of each 128-byte column line; the
         // SWIZZLE_128B layout stores chunk k of line c at chunk position k ^ (c & 7)
         const char* box = reinterpret_cast<const char*>(tile) + ((r4 * DPE) / 16) * BOX_BYTES;
@@ -411,9 +475,22 @@ __device__ double tile_engine(const T* __restrict__ A, int64_t lda, int n, const
 #pragma unroll
         for (int h = 0; h < 4; ++h) xr[h] = xfix(I * TB + r4 + h, tile[TB * TB + r4 + h]);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);          // this warp is done with the stage
+        if (lane == 0) mbar_arrive(&empty[stc]);          // this warp is done with the stage
+        if (diag) {
+          // the box also brought the (ignored) lower triangle: keep r < c, make the diagonal real
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int r = r4 + h, c = lane + 32 * q;
+              if (r > c) a[h][q] = zero_<T>();
+              else if (r == c) a[h][q] = from_real<T>(real_(a[h][q]));
+            }
+        }
       } else {
-        // diagonal tile (or ring disabled): masked loads straight from global memory
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stc]);          // the stage carried only the descriptor
+        // masked loads straight from global memory
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = lane + 32 * q, gc = J * TB + c;
@@ -459,23 +536,31 @@ __device__ double tile_engine(const T* __restrict__ A, int64_t lda, int n, const
         if (!diag) Pd[(int64_t)J * ldp + I * TB + r4 + h] = accd[0];     // off-diagonal tile: all 64 rows are < n
         else es.ydiag[r4 + h] = accd[0];
       }
-      if (last) {
+      if (fl & MF_LAST) {
         // strip end: combine the transposed sums of the 16 warps (+ the diagonal tile's direct part) -> Pt[band]
         es.yt[warp][lane] = acct[0];
         es.yt[warp][lane + 32] = acct[1];
+        const double vs = warp_sum(vav);
+        if (lane == 0) es.vred[warp] = vs;
         consumer_barrier();
         if (tid < TB) {
           T s = diag ? es.ydiag[tid] : zero_<T>();
 #pragma unroll
           for (int w = 0; w < NW; ++w) s = add_(s, es.yt[w][tid]);
+          const int band = ((diag ? J : I) * um.rcpC) >> 16;
           if (J * TB + tid < n) Pt[(int64_t)band * ldp + J * TB + tid] = s;
+        } else if (tid == TB) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) s += es.vred[w];
+          vavunit[unit] = s;
         }
         consumer_barrier();
       }
     }
   }
+  rs.stage = st;
   __syncthreads();
-  return vav;
 }
 
 // sum of the partials belonging to row r of an order-n product computed with strip length C
@@ -508,21 +593,33 @@ __device__ __forceinline__ T* ex_slot(const TrdP<T>& p, int dst, int q, unsigned
   return p.peer_w[dst] + ((int64_t)q * 2 + par) * p.wstride;
 }
 
+// profiling aid: CTA 0 / thread 0 records a globaltimer stamp in slot k of panel column c
+template <typename T>
+__device__ __forceinline__ void tstamp(const TrdP<T>& p, int c, int k) {
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && c >= 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(size_t)(p.i0 + c) * TRSLOTS + k] = t;
+  }
+}
+
 // ---- stand-alone symv/hemv (eigb200_dsymv / eigb200_zhemv): the same engine + a gather kernel -------------
 template <typename T>
 __global__ void __launch_bounds__(NTT, 1) hemv_tiles_kernel(const __grid_constant__ CUtensorMap tmap,
                                                             const T* __restrict__ A, int64_t lda, int n,
                                                             const T* __restrict__ xpad, T* Pd, T* Pt, int64_t ldp, int C,
-                                                            int tma, int vec_ok) {
+                                                            int tma, double* vavunit, unsigned* qctr) {
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ EngineSmem<T> es;
   __shared__ __align__(8) uint64_t full[8], empty[8];
+  __shared__ TileMeta meta[8];
   T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
-  RingState rs; rs.stage = 0; rs.par = (threadIdx.x >= NT) ? 0xffffffffu : 0u;
-  if (tma) ring_init<T>(ring, full, empty, rs);
+  RingState rs;
+  ring_init(full, empty, RingCfg<T>::STAGES, rs);
   auto xfix = [n](int r, T raw) -> T { return r < n ? raw : zero_<T>(); };
-  tile_engine<T>(A, lda, n, xpad, xfix, Pd, Pt, ldp, blockIdx.x, gridDim.x, C, tma != 0, vec_ok, ring, full, empty, rs, es,
-                 &tmap);
+  const UnitMap um = engine_prepare<T>(n, C, 0, 1, es);
+  engine_run<T>(um, A, lda, n, xpad, xfix, Pd, Pt, ldp, vavunit, qctr, blockIdx.x, gridDim.x, tma != 0, ring, full, empty,
+                meta, rs, es, &tmap, nullptr, 0, 1);
 }
 template <typename T>
 __global__ void hemv_reduce_kernel(const T* Pd, const T* Pt, int64_t ldp, int n, int C, T* y) {
@@ -538,20 +635,26 @@ __global__ void pad_copy_kernel(const T* x, int n, T* xpad, int npad) {
 // =====================================================================================================
 // Panel phases
 // =====================================================================================================
+// Phase A (row-parallel): with the partial sums of the previous column's product (order jp = j+1) complete,
+//   * finish  W(:, c+1) = tau (w_raw - W z1 - V z2) + alpha' v   and store the reflector v itself in A(:, j+1),
+//   * bring column c (global j) up to date with the panel's reflectors, write it unscaled to xbuf, partial norms.
+// This phase is bound by instruction issue and L2 latency, not by bandwidth, so the work is split by role:
+//   * the 16 worker warps own one contiguous block of rows per CTA (one row per lane, the warps of a row group
+//     split the partial-sum slots and the panel columns) and issue all their independent loads up front;
+//   * warp 16 (the TMA producer, idle here) gathers everything that is common to all rows -- z1, z2, row j of V
+//     and W, the slots of row j, tau, scale -- and derives rho, alpha', W(j, c+1) while the workers run their
+//     V/W loop; the results travel through shared memory.
 template <typename T, bool MG>
-__device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
+__device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc& cd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
   const int nbp = p.nbp;
   const int j = p.i0 + c;                       // column brought up to date in this phase (c may be -1)
   const int jp = j + 1;                         // order of the product done for column c+1
-  const bool have_prev = (c + 1 <= nbp - 1) && (jp >= 1) && !(c == -1 && p.i0 == 0);
   const int cprev = c + 1;
-  const int Pn = MG ? p.P : 1;                  // compile-time 1 in the single-GPU kernel
-  const int Cp = strip_len(jp, G, Pn);          // strip length used by the previous phase B
-  T tau_p = zero_<T>();
-  double alpha_p = 0.0;
+  const bool have_prev = (cprev <= nbp - 1) && (jp >= 1);
   const bool mg = MG && p.P > 1;
+  PhaseASmem<T>& S = sm.u.a;
   const unsigned long long seqp = have_prev ? col_seq(p, cprev) : 0ull;
   const unsigned parp = (unsigned)(seqp & 1ull);
   if (mg && have_prev) {
@@ -560,130 +663,217 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
       const unsigned long long* fl = p.peer_flag[p.rank] + tid;
       unsigned long long spins = 0;
       while (ld_acquire_sys(fl) < seqp) {
-        if (++spins > (1ull << 26)) { atomicExch(p.status, 78); break; }
+        if (++spins > (1ull << 25)) { atomicExch(p.status, 78); __trap(); }
       }
     }
     __syncthreads();
   }
+  // ---- rows [rbeg, rend) of this CTA in groups of 32 (one row per lane); GC = 2^gcs groups run side by side,
+  //      each split over WPG = 16 / GC warps
+  const int nrows = jp > 0 ? jp : 0;
+  int R;
+  if (have_prev) R = cd.R;
+  else { R = (nrows + G - 1) / G; R = (R + 7) & ~7; }          // first column of a panel: once per launch
+  const int Tn = cd.Tn;                                        // (meaningful when have_prev)
+  const int rbeg = cta * R;
+  const int rend = nrows < rbeg + R ? nrows : rbeg + R;
+  const int ngrp = rend > rbeg ? (rend - rbeg + 31) >> 5 : 0;
+  const int gcs = ngrp <= 1 ? 0 : (ngrp == 2 ? 1 : 2);
+  const int GC = 1 << gcs, wpgs = 4 - gcs, WPG = 1 << wpgs;
+  const int grp = warp >> wpgs, sub = warp & (WPG - 1);        // warp 16: grp == GC -> no row work
 
-  if (have_prev) {
-    // -- z1 = V^H v, z2 = W^H v from the row-chunk partials; v^H A v from the per-CTA partials
-    const int zch = zchunk_rows(jp);
-    const int nzu = (jp + zch - 1) / zch;
-    const int nf = nbp - 1 - cprev;             // finished columns cc in (cprev, nbp)
-    for (int q = tid; q < 2 * nf; q += NT) {
-      const int which = q / nf, cc = cprev + 1 + (q % nf);
-      const T* zp = p.zpart + (int64_t)which * NBMAX + cc;
-      T s0 = zero_<T>(), s1 = zero_<T>(), s2 = zero_<T>(), s3 = zero_<T>();
-      int u = 0;
-      for (; u + 3 < nzu; u += 4) {
-        T a = ldcg_(zp + (int64_t)u * 2 * NBMAX), b = ldcg_(zp + (int64_t)(u + 1) * 2 * NBMAX);
-        T cc2 = ldcg_(zp + (int64_t)(u + 2) * 2 * NBMAX), d = ldcg_(zp + (int64_t)(u + 3) * 2 * NBMAX);
-        s0 = add_(s0, a); s1 = add_(s1, b); s2 = add_(s2, cc2); s3 = add_(s3, d);
-      }
-      for (; u < nzu; ++u) s0 = add_(s0, ldcg_(zp + (int64_t)u * 2 * NBMAX));
-      (which ? sm.u.a.z2 : sm.u.a.z1)[cc] = add_(add_(s0, s1), add_(s2, s3));
-    }
-    // row j of V and W (finished columns); rowW[cprev] is filled below
-    for (int cc = cprev + 1 + tid; cc < nbp; cc += NT) {
-      sm.u.a.rowV[cc] = ldcg_(p.A + j + (int64_t)(p.i0 + cc) * p.lda);
-      sm.u.a.rowW[cc] = ldcg_(p.W + j + (int64_t)cc * p.ldw);
-    }
-    if (tid == 0) sm.u.a.rowV[cprev] = from_real<T>(1.0);   // unit element of v_{c+1} sits in row j
-    double vv = 0.0;
-    if (!mg) { for (int g = tid; g < G; g += NT) vv += __ldcg(p.vavpart + g); }
-    else if (tid < p.P) vv = real_(ldcg_(ex_slot(p, p.rank, tid, parp) + p.wstride - 1));
-    vv = block_sum<double>(vv, sm.dscal);    // (contains __syncthreads: z1/z2/rowV/rowW visible after it)
-    // rho = v^H A v - 2 Re(z1^H z2)
-    double zz = 0.0;
-    for (int cc = cprev + 1 + tid; cc < nbp; cc += NT) {
-      T t = zero_<T>(); fmac_(t, sm.u.a.z1[cc], sm.u.a.z2[cc]);
-      zz += real_(t);
-    }
-    __syncthreads();
-    zz = block_sum<double>(zz, sm.dscal);
-    tau_p = ldcg_(p.tau + j);                   // written by CTA 0 in the previous phase B (before a barrier)
-    const double rho = vv - 2.0 * zz;
-    alpha_p = -0.5 * abs2_(tau_p) * rho;
-    // row j of the new W column: u_j = wraw_j - sum_cc (W(j,cc) z1(cc) + V(j,cc) z2(cc))
-    T part = zero_<T>();
-    for (int cc = cprev + 1 + tid; cc < nbp; cc += NT) {
-      fma_(part, sm.u.a.rowW[cc], sm.u.a.z1[cc]);
-      fma_(part, sm.u.a.rowV[cc], sm.u.a.z2[cc]);
-    }
-    __syncthreads();
-    part = block_sum<T>(part, sm.tred);
-    if (warp == 0) {
-      // wraw_j: lane-strided gather of the partials of row j, fixed order
-      const int Tn = (jp + TB - 1) / TB, I = j / TB;
-      T wr = zero_<T>();
-      if (!mg) {
-        for (int J = I + 1 + lane; J < Tn; J += 32) wr = add_(wr, ldcg_(p.Pd + (int64_t)J * p.ldp + j));
-        for (int k = lane; k <= I / Cp; k += 32) wr = add_(wr, ldcg_(p.Pt + (int64_t)k * p.ldp + j));
-      } else if (lane < p.P) {
-        wr = ldcg_(ex_slot(p, p.rank, lane, parp) + j);
-      }
-      wr = warp_sum(wr);
-      if (lane == 0) {
-        T w = mul_(tau_p, sub_(wr, part));
-        sm.u.a.rowW[cprev] = add_(w, from_real<T>(alpha_p));    // + alpha' * v(j), v(j) = 1
-      }
-    }
-    __syncthreads();
-  }
-
-  // -- row-parallel part: groups of 32 consecutive rows are dealt to the CTAs; inside a CTA AW warps split the
-  //    panel columns and the partial-sum slots of those rows, warp 0 combines and finishes them
   double nrm = 0.0;
-  const int nrows = (c >= 0) ? (j + 1) : jp;     // c == -1: only finish W(:, 0), rows [0, i0)
-  const int ngroups = (nrows + 31) / 32;
-  const int Tn = (jp + TB - 1) / TB;
-  for (int g = cta; g < ngroups; g += G) {
-    const int r = g * 32 + lane;
-    const bool rv = r < nrows;
-    if (warp < AW) {
-      T t1 = zero_<T>(), t2 = zero_<T>(), wr = zero_<T>();
-      if (rv) {
-        for (int cc = cprev + 1 + warp; cc < nbp; cc += AW) {
-          const T vv = ldcg_(p.A + r + (int64_t)(p.i0 + cc) * p.lda);
-          const T ww = ldcg_(p.W + r + (int64_t)cc * p.ldw);
-          if (have_prev) { fma_(t1, ww, sm.u.a.z1[cc]); fma_(t1, vv, sm.u.a.z2[cc]); }
-          if (c >= 0) { fma_(t2, vv, conj_(sm.u.a.rowW[cc])); fma_(t2, ww, conj_(sm.u.a.rowV[cc])); }
-        }
-        if (have_prev) {
-          if (!mg) {
-            const int I = (g * 32) / TB;
-            const int nd = Tn - (I + 1);                // direct slots J = I+1 .. Tn-1
-            const int nt = I / Cp + 1;                  // band slots k = 0 .. I/Cp
-            for (int q = warp; q < nd + nt; q += AW) {
-              const T* src = (q < nd) ? (p.Pd + (int64_t)(I + 1 + q) * p.ldp) : (p.Pt + (int64_t)(q - nd) * p.ldp);
-              wr = add_(wr, ldcg_(src + r));
-            }
-          } else {
-            for (int q = warp; q < p.P; q += AW) wr = add_(wr, ldcg_(ex_slot(p, p.rank, q, parp) + r));
+  for (int g0 = 0, round = 0; round == 0 || g0 < ngrp; g0 += GC, ++round) {
+    const int r = rbeg + (g0 + grp) * 32 + lane;
+    const bool rv = warp < NW && (g0 + grp) < ngrp && r < rend;
+    T wr = zero_<T>(), xb = zero_<T>(), acol = zero_<T>();
+    T pv[4], pw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { pv[k] = zero_<T>(); pw[k] = zero_<T>(); }
+    if (round > 0) __syncthreads();              // ared is reused
+    if (warp == NW) {
+      // ===================== scalar warp (round 0 only) =====================
+      if (round == 0 && have_prev) {
+        const T tau_p = ldcg_(p.tau + j);        // written by CTA 0 in the previous phase B (before a barrier)
+        const T scale_p = ldcg_(p.scale_slot);
+        T a1[4], a2[4], a3[4], a4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int cc = cprev + 1 + lane + 32 * k;
+          a1[k] = a2[k] = a3[k] = a4[k] = zero_<T>();
+          if (cc < nbp) {
+            a1[k] = ldcg_(p.zfin + cc); a2[k] = ldcg_(p.zfin + NBMAX + cc);
+            a3[k] = ldcg_(p.A + j + (int64_t)(p.i0 + cc) * p.lda); a4[k] = ldcg_(p.W + j + (int64_t)cc * p.ldw);
           }
         }
-      }
-      T* ar = sm.u.a.ared + (warp * 32 + lane) * 3;
-      ar[0] = t1; ar[1] = t2; ar[2] = wr;
-    }
-    __syncthreads();
-    if (warp == 0 && rv) {
-      T t1 = zero_<T>(), t2 = zero_<T>(), wr = zero_<T>();
+        // partial-sum slots of row j (or the P exchange slots)
+        T wj = zero_<T>();
+        double vx = 0.0;
+        if (!mg) {
+          const int ndj = cd.ndj, nsj = cd.nsj, Ij = j >> 6;
+          for (int q0 = lane; q0 < nsj; q0 += 128) {
+            T v[4];
 #pragma unroll
-      for (int w = 0; w < AW; ++w) {
-        const T* a2 = sm.u.a.ared + (w * 32 + lane) * 3;
-        t1 = add_(t1, a2[0]); t2 = add_(t2, a2[1]); wr = add_(wr, a2[2]);
+            for (int k = 0; k < 4; ++k) {
+              const int q = q0 + 32 * k;
+              const T* src = (q < ndj) ? (p.Pd + (int64_t)(Ij + 1 + q) * p.ldp) : (p.Pt + (int64_t)(q - ndj) * p.ldp);
+              v[k] = q < nsj ? ldcg_(src + j) : zero_<T>();
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wj = add_(wj, v[k]);
+          }
+        } else if (lane < p.P) {
+          wj = ldcg_(ex_slot(p, p.rank, lane, parp) + j);
+          vx = real_(ldcg_(ex_slot(p, p.rank, lane, parp) + p.wstride - 1));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int cc = cprev + 1 + lane + 32 * k;
+          if (cc < nbp) { S.z1[cc] = a1[k]; S.z2[cc] = a2[k]; S.rowV[cc] = a3[k]; S.rowW[cc] = a4[k]; }
+        }
+        // z1^H z2 and the row-j correction  W(j,:) z1 + V(j,:) z2
+        double zz = 0.0;
+        T part = zero_<T>();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          T t = zero_<T>(); fmac_(t, a1[k], a2[k]);
+          zz += real_(t);
+          fma_(part, a4[k], a1[k]);
+          fma_(part, a3[k], a2[k]);
+        }
+        zz = warp_sum(zz);
+        part = warp_sum(part);
+        wj = warp_sum(wj);
+        vx = warp_sum(vx);
+        __syncthreads();                          // (#1) workers' shares of v^H A v are in dscal
+        double vv = vx;
+        if (!mg) {
+#pragma unroll
+          for (int w = 0; w < NW; ++w) vv += sm.dscal[w];
+        }
+        // rho = v^H A v - 2 Re(z1^H z2), alpha' = -1/2 |tau|^2 rho, W(j, c+1) = tau (w_j - part) + alpha' (v(j) = 1)
+        const double rho = vv - 2.0 * zz;
+        const double alpha_p = -0.5 * abs2_(tau_p) * rho;
+        if (lane == 0) {
+          S.s_tau = tau_p; S.s_scale = scale_p; S.s_alpha = alpha_p;
+          S.s_wj = add_(mul_(tau_p, sub_(wj, part)), from_real<T>(alpha_p));
+        }
+      } else if (round == 0) {
+        __syncthreads();                          // (#1)
+      }
+      __syncthreads();                            // (#2)
+      continue;
+    }
+    // ===================== worker warps =====================
+    if (rv && sub == 0) {
+      if (have_prev) xb = ldcg_(p.xbuf + r);
+      if (c >= 0) acol = ldcg_(p.A + r + (int64_t)j * p.lda);
+    }
+    if (have_prev) {
+      if (round == 0 && !mg) {
+        // this thread's share of the per-unit v^H A v slots
+        const int total = cd.total;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (tid < total) v0 = __ldcg(p.vavunit + tid);
+        if (tid + NT < total) v1 = __ldcg(p.vavunit + tid + NT);
+        if (tid + 2 * NT < total) v2 = __ldcg(p.vavunit + tid + 2 * NT);
+        for (int t = tid + 3 * NT; t < total; t += NT) v0 += __ldcg(p.vavunit + t);
+        const double vs = warp_sum((v0 + v1) + v2);
+        if (lane == 0) sm.dscal[warp] = vs;
+      }
+      if (rv) {
+        if (!mg) {
+          // partial-sum slots of row r: direct J = I+1 .. Tn-1, then bands k = 0 .. I/Cp; this warp takes every WPG-th
+          const int I = r >> 6;
+          const int nd = Tn - (I + 1);
+          const int nt = ((I * cd.rcpC) >> 16) + 1;
+          const int64_t step = (int64_t)p.ldp << wpgs;
+          {
+            const T* ptr = p.Pd + (int64_t)(I + 1 + sub) * p.ldp + r;
+            int cnt = nd > sub ? (nd - sub + WPG - 1) >> wpgs : 0;
+            for (; cnt > 0; cnt -= 4) {
+              const T v0 = ldcg_(ptr);
+              const T v1 = cnt > 1 ? ldcg_(ptr + step) : zero_<T>();
+              const T v2 = cnt > 2 ? ldcg_(ptr + 2 * step) : zero_<T>();
+              const T v3 = cnt > 3 ? ldcg_(ptr + 3 * step) : zero_<T>();
+              ptr += 4 * step;
+              wr = add_(wr, add_(add_(v0, v1), add_(v2, v3)));
+            }
+          }
+          {
+            const T* ptr = p.Pt + (int64_t)sub * p.ldp + r;
+            int cnt = nt > sub ? (nt - sub + WPG - 1) >> wpgs : 0;
+            for (; cnt > 0; cnt -= 4) {
+              const T v0 = ldcg_(ptr);
+              const T v1 = cnt > 1 ? ldcg_(ptr + step) : zero_<T>();
+              const T v2 = cnt > 2 ? ldcg_(ptr + 2 * step) : zero_<T>();
+              const T v3 = cnt > 3 ? ldcg_(ptr + 3 * step) : zero_<T>();
+              ptr += 4 * step;
+              wr = add_(wr, add_(add_(v0, v1), add_(v2, v3)));
+            }
+          }
+        } else {
+          for (int q = sub; q < p.P; q += WPG) wr = add_(wr, ldcg_(ex_slot(p, p.rank, q, parp) + r));
+        }
+      }
+    }
+    // the first four (V, W) pairs of this warp's panel columns are in flight across the barrier
+    if (rv) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cc = cprev + 1 + sub + (k << wpgs);
+        if (cc < nbp) {
+          pv[k] = ldcg_(p.A + r + (int64_t)(p.i0 + cc) * p.lda);
+          pw[k] = ldcg_(p.W + r + (int64_t)cc * p.ldw);
+        }
+      }
+    }
+    tstamp(p, c, 5);
+    if (round == 0) __syncthreads();              // (#1) z1, z2, rowV, rowW are in shared memory
+    tstamp(p, c, 7);
+    T t1 = zero_<T>(), t2 = zero_<T>();
+    if (rv) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cc = cprev + 1 + sub + (k << wpgs);
+        if (cc < nbp) {
+          if (have_prev) { fma_(t1, pw[k], S.z1[cc]); fma_(t1, pv[k], S.z2[cc]); }
+          if (c >= 0) { fma_(t2, pv[k], conj_(S.rowW[cc])); fma_(t2, pw[k], conj_(S.rowV[cc])); }
+        }
+      }
+#pragma unroll 2
+      for (int cc = cprev + 1 + sub + (4 << wpgs); cc < nbp; cc += WPG) {
+        const T vv = ldcg_(p.A + r + (int64_t)(p.i0 + cc) * p.lda);
+        const T ww = ldcg_(p.W + r + (int64_t)cc * p.ldw);
+        if (have_prev) { fma_(t1, ww, S.z1[cc]); fma_(t1, vv, S.z2[cc]); }
+        if (c >= 0) { fma_(t2, vv, conj_(S.rowW[cc])); fma_(t2, ww, conj_(S.rowV[cc])); }
+      }
+    }
+    {
+      T* ar = S.ared + (warp * 32 + lane) * 2;
+      ar[0] = sub_(wr, t1); ar[1] = t2;
+    }
+    tstamp(p, c, 9);
+    __syncthreads();                              // (#2) also: the scalar warp's results
+    tstamp(p, c, 10);
+    if (rv && sub == 0) {
+      T u = zero_<T>(), t2s = zero_<T>();
+      for (int w = 0; w < WPG; ++w) {
+        const T* a2 = S.ared + (((grp << wpgs) + w) * 32 + lane) * 2;
+        u = add_(u, a2[0]); t2s = add_(t2s, a2[1]);
       }
       if (have_prev) {
-        const T vnew = ldcg_(p.A + r + (int64_t)(j + 1) * p.lda);
-        T wnew = mul_(tau_p, sub_(wr, t1));
-        wnew = add_(wnew, scale_(vnew, alpha_p));
+        const T tau_p = S.s_tau, scale_p = S.s_scale, wjfin = S.s_wj;
+        const double alpha_p = S.s_alpha;
+        // the reflector generated in the previous phase B: v(r) = scale * x(r), v(j) = 1
+        const T vnew = (r == j) ? from_real<T>(1.0) : mul_(scale_p, xb);
+        p.A[r + (int64_t)(j + 1) * p.lda] = vnew;
+        const T wnew = (r == j) ? wjfin : add_(mul_(tau_p, u), scale_(vnew, alpha_p));
         p.W[r + (int64_t)cprev * p.ldw] = wnew;
-        if (c >= 0) { fma_(t2, vnew, conj_(sm.u.a.rowW[cprev])); fma_(t2, wnew, conj_(sm.u.a.rowV[cprev])); }
+        if (c >= 0) { fma_(t2s, vnew, conj_(wjfin)); t2s = add_(t2s, wnew); }    // V(j, c+1) = 1
       }
       if (c >= 0) {
-        T a = sub_(ldcg_(p.A + r + (int64_t)j * p.lda), t2);
+        T a = sub_(acol, t2s);
         if (r == j) {
           a = from_real<T>(real_(a));
           p.d[j] = real_(a);
@@ -695,91 +885,110 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
         }
       }
     }
-    __syncthreads();
   }
-  if (c >= 0) {
-    __syncthreads();
-    nrm = block_sum<double>(nrm, sm.dscal);
-    if (tid == 0) p.npart[cta] = nrm;
-  }
+  // per-warp partial norms; the caller (grid barrier or the stand-alone kernel) adds them up after a CTA barrier
+  nrm = warp_sum(nrm);
+  if (lane == 0) sm.nred[warp] = nrm;
 }
 
+// sum of the per-warp partial norms of phase A -> npart[cta]; one thread, after a CTA barrier
+template <typename T>
+__device__ __forceinline__ void store_npart(const TrdP<T>& p, const PanelSmem<T>& sm) {
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < NWT; ++w) s += sm.nred[w];
+  p.npart[blockIdx.x] = s;
+}
+
+// Phase B (tile phase).  Warp 0 derives the Householder scalars (fixed summation order => identical in every
+// CTA) while the producer warp already fetches tiles (they do not depend on v; x travels unscaled and is scaled
+// when it is used); the consumer warps of the CTAs at the far end of the grid then take the z-dot units
+// (z1 = V^H v, z2 = W^H v, one (matrix, column) pair per CTA, complete dot product) before joining the tile queue,
+// which absorbs the difference.  Returns the number of tile units of this product.
 template <typename T, bool MG>
-__device__ void phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingState& rs, const CUtensorMap* tmap) {
+__device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingState& rs, const CUtensorMap* tmap,
+                       const ColDesc& cd, ColDesc* next_cd) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
   const int j = p.i0 + c;            // order of the product; reflector index j-1
-  if (j <= 0) return;
-  // -- Householder scalars (every CTA, same summation order => identical values everywhere)
-  double x2 = 0.0;
-  for (int g = tid; g < G; g += NT) x2 += __ldcg(p.npart + g);
-  x2 = block_sum<double>(x2, sm.dscal);
-  const T alpha = ldcg_(p.alpha_slot);
-  double beta; T tau, scale;
-  larfg_scalars(alpha, x2, beta, tau, scale);
-  if (cta == 0 && tid == 0) { p.e[j - 1] = beta; p.tau[j - 1] = tau; }
-  // -- store v in A(:, j) (nobody reads column j in this phase)
-  if (tid < NT)
-  for (int r = cta * NT + tid; r < j; r += G * NT) {
-    T v = (r == j - 1) ? from_real<T>(1.0) : mul_(scale, ldcg_(p.xbuf + r));
-    p.A[r + (int64_t)j * p.lda] = v;
+  if (j <= 0) return 0;
+  const int Pn = MG ? p.P : 1, rk = MG ? p.rank : 0;
+  UnitMap um;
+  if (Pn > 1) {
+    um = engine_prepare<T>(j, cd.C, rk, Pn, sm.u.e);      // tabulates this rank's units (CTA barriers inside)
+  } else {
+    um.Tn = cd.Tn; um.C = cd.C; um.rank = 0; um.P = 1; um.TnO = cd.Tn; um.KB = cd.KB; um.NF = cd.NF; um.total = cd.total;
+    um.bstart = nullptr;
   }
+  um.rcpC = cd.rcpC;
+  T scale = from_real<T>(1.0);
+  if (warp < NW) {
+    if (warp == 0) {
+      double xs[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) { const int g = lane + 32 * k; xs[k] = g < G ? __ldcg(p.npart + g) : 0.0; }
+      const T alpha = ldcg_(p.alpha_slot);
+      double x2 = ((xs[0] + xs[1]) + (xs[2] + xs[3])) + xs[4];
+      for (int g = lane + 160; g < G; g += 32) x2 += __ldcg(p.npart + g);
+      x2 = warp_sum(x2);
+      double beta; T tau;
+      larfg_scalars(alpha, x2, beta, tau, scale);
+      if (lane == 0) {
+        sm.hh_scale = scale;
+        if (cta == 0) { p.e[j - 1] = beta; p.tau[j - 1] = tau; *p.scale_slot = scale; }
+      }
+    }
+    consumer_barrier();
+    scale = sm.hh_scale;
+  }
+  tstamp(p, c, 12);
   auto xfix = [j, scale](int r, T raw) -> T {
     if (r >= j) return zero_<T>();
     if (r == j - 1) return from_real<T>(1.0);
     return mul_(scale, raw);
   };
-  auto xval = [&](int r) -> T { return xfix(r, r < j ? p.xbuf[r] : zero_<T>()); };
-  // -- partial dots z1 = V^H v, z2 = W^H v: unit = (row chunk u, group of NW (which, cc) pairs), one pair per warp
+  // -- z1 = V^H v, z2 = W^H v: pair q = (which, cc) is done completely by the consumer warps of CTA G-1-q
   const int nf = p.nbp - 1 - c;      // finished columns cc in (c, nbp)
-  if (nf > 0) {
-    const int zch = zchunk_rows(j);
-    const int nzch = (j + zch - 1) / zch;
-    const int ngrp = (2 * nf + NW - 1) / NW;
-    T* xs = sm.u.a.ared;               // 512-row slice of v staged in shared memory (phase-A scratch is free here)
-    // start at the far end of the CTA range so that these units do not pile onto the CTAs with the longest strips
-    for (int unit = (G - 1 - cta); unit < nzch * ngrp; unit += G) {
-      const int u = unit / ngrp, grp = unit % ngrp;
-      const int q = grp * NW + warp;
-      const bool active = warp < NW && q < 2 * nf;
-      const int which = active ? q / nf : 0, cc = active ? c + 1 + (q % nf) : 0;
+  if (nf > 0 && warp < NW) {
+    T* zr = sm.u.e.ydiag;            // per-warp partial dots (the engine's scratch is not in use yet)
+    for (int q = G - 1 - cta; q < 2 * nf; q += G) {
+      const int which = q >= nf ? 1 : 0, cc = c + 1 + (q - which * nf);
       const T* col = which ? (p.W + (int64_t)cc * p.ldw) : (p.A + (int64_t)(p.i0 + cc) * p.lda);
-      T sacc = zero_<T>();
-      for (int r0 = u * zch; r0 < min(j, (u + 1) * zch); r0 += ZROWS) {
-        const int rows = min(ZROWS, min(j, (u + 1) * zch) - r0);
-        __syncthreads();
-        for (int i = tid; i < rows; i += blockDim.x) xs[i] = xval(r0 + i);
-        __syncthreads();
-        if (active) {
-          // 512 rows = 16 loads per lane, issued 8 at a time (this loop is L2-latency bound)
-          for (int i0 = lane; i0 < rows; i0 += 256) {
-            T cv[8];
+      T s0 = zero_<T>(), s1 = zero_<T>();
+      for (int r0 = tid; r0 < j; r0 += 4 * NT) {
+        T cv[4], xv[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const int i = i0 + 32 * k; cv[k] = i < rows ? ldcg_(col + r0 + i) : zero_<T>(); }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const int i = i0 + 32 * k; if (i < rows) fmac_(sacc, cv[k], xs[i]); }
-          }
+        for (int k = 0; k < 4; ++k) {
+          const int r = r0 + k * NT;
+          cv[k] = r < j ? ldcg_(col + r) : zero_<T>();
+          xv[k] = r < j ? ldcg_(p.xbuf + r) : zero_<T>();
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fmac_((k & 1) ? s1 : s0, cv[k], xfix(r0 + k * NT, xv[k]));
       }
-      if (active) {
-        sacc = warp_sum(sacc);
-        if (lane == 0) p.zpart[((int64_t)u * 2 + which) * NBMAX + cc] = sacc;
+      s0 = warp_sum(add_(s0, s1));
+      if (lane == 0) zr[warp] = s0;
+      consumer_barrier();
+      if (tid == 0) {
+        T s = zero_<T>();
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s = add_(s, zr[w]);
+        p.zfin[which * NBMAX + cc] = s;
       }
+      consumer_barrier();
     }
   }
+  tstamp(p, c, 13);
   // -- the tile engine: w_raw partials and v^H A v
-  __syncthreads();     // phase-A scratch is dead from here on: the engine overlays it
-  const int Pn = MG ? p.P : 1, rk = MG ? p.rank : 0;
-  double vav = tile_engine<T>(p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, cta, G, strip_len(j, G, Pn),
-                              p.use_tma != 0, p.vec_ok, ring, sm.full, sm.empty, rs, sm.u.e, tmap, rk, Pn);
-  vav = block_sum<double>(vav, sm.dscal);
-  if (tid == 0) p.vavpart[cta] = vav;
+  engine_run<T>(um, p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, p.vavunit, p.qctr + c, cta, G, p.use_tma != 0, ring,
+                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn);
+  return um.total;
 }
 
 // Phase C (multi-GPU only): reduce this rank's partial sums to one vector w_p(0:j) and push it, together with the
 // local v^H A v, into the exchange buffer of EVERY rank (peer stores over NVLink); the caller then signals.
 template <typename T>
-__device__ void phase_c(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
+__device__ void phase_c(const TrdP<T>& p, int c, PanelSmem<T>& sm, int total_units) {
   const int tid = threadIdx.x;
   const int G = gridDim.x, cta = blockIdx.x;
   const int j = p.i0 + c;
@@ -819,7 +1028,7 @@ __device__ void phase_c(const TrdP<T>& p, int c, PanelSmem<T>& sm) {
   }
   if (cta == 0) {
     double vv = 0.0;
-    for (int g = tid; g < G; g += NT) { if (tid < NT) vv += __ldcg(p.vavpart + g); }
+    for (int t = tid; t < total_units; t += NTT) vv += __ldcg(p.vavunit + t);
     vv = block_sum<double>(vv, sm.dscal);
     if (tid < p.P) ex_slot(p, tid, p.rank, par)[p.wstride - 1] = from_real<T>(vv);
   }
@@ -830,33 +1039,28 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ PanelSmem<T> sm;
   T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
-  RingState rs; rs.stage = 0; rs.par = (threadIdx.x >= NT) ? 0xffffffffu : 0u;
-  if (p.use_tma) ring_init<T>(ring, sm.full, sm.empty, rs);
+  RingState rs;
+  const int Pn = MG ? p.P : 1;
+  if (threadIdx.x == NT) compute_desc(sm.cd[(p.nbp - 1) & 1], p.i0 + p.nbp - 1, gridDim.x, Pn);
+  ring_init(sm.full, sm.empty, RingCfg<T>::STAGES, rs);      // (CTA barrier inside)
   unsigned target = 0;
-  const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-  auto stamp = [&](int c, int k) {
-    if (tr) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      p.trace[(size_t)(p.i0 + c) * 5 + k] = t;
-    }
-  };
+  auto stamp = [&](int c, int k) { tstamp(p, c, k); };
   for (int c = p.nbp - 1; c >= -1; --c) {
     if (c >= 0) stamp(c, 0);
-    phase_a<T, MG>(p, c, sm);
+    phase_a<T, MG>(p, c, sm, sm.cd[(c + 1) & 1]);
     if (c < 0) break;
     stamp(c, 1);
     target += gridDim.x;
-    grid_barrier(p.barrier, target, p.status);
+    grid_barrier(p.barrier, target, p.status, false, [&]() { store_npart(p, sm); });
     stamp(c, 2);
-    phase_b<T, MG>(p, c, sm, ring, rs, &tmap);
+    const int total_units = phase_b<T, MG>(p, c, sm, ring, rs, &tmap, sm.cd[c & 1], &sm.cd[(c + 1) & 1]);
     stamp(c, 3);
     target += gridDim.x;
-    grid_barrier(p.barrier, target, p.status);
+    grid_barrier(p.barrier, target, p.status, false, []() {});
     if (MG && p.P > 1 && p.i0 + c > 0) {
-      phase_c<T>(p, c, sm);
+      phase_c<T>(p, c, sm, total_units);
       target += gridDim.x;
-      grid_barrier(p.barrier, target, p.status, true);     // system-scope fences: peer stores are complete
+      grid_barrier(p.barrier, target, p.status, true, []() {});     // system-scope fences: peer stores are complete
       if (blockIdx.x == 0 && threadIdx.x < p.P) {
         __threadfence_system();
         st_release_sys(p.peer_flag[threadIdx.x] + p.rank, col_seq(p, c));
@@ -868,16 +1072,21 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
 template <typename T>
 __global__ void __launch_bounds__(NTT, 1) phase_a_kernel(TrdP<T> p, int c) {
   __shared__ PanelSmem<T> sm;
-  phase_a<T, false>(p, c, sm);
+  if (threadIdx.x == 0) compute_desc(sm.cd[0], p.i0 + c + 1, gridDim.x, 1);
+  __syncthreads();
+  phase_a<T, false>(p, c, sm, sm.cd[0]);
+  __syncthreads();
+  if (threadIdx.x == 0 && c >= 0) store_npart(p, sm);
 }
 template <typename T>
 __global__ void __launch_bounds__(NTT, 1) phase_b_kernel(const __grid_constant__ CUtensorMap tmap, TrdP<T> p, int c) {
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
   __shared__ PanelSmem<T> sm;
   T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
-  RingState rs; rs.stage = 0; rs.par = (threadIdx.x >= NT) ? 0xffffffffu : 0u;
-  if (p.use_tma) ring_init<T>(ring, sm.full, sm.empty, rs);
-  phase_b<T, false>(p, c, sm, ring, rs, &tmap);
+  RingState rs;
+  if (threadIdx.x == NT) compute_desc(sm.cd[0], p.i0 + c, gridDim.x, 1);
+  ring_init(sm.full, sm.empty, RingCfg<T>::STAGES, rs);
+  phase_b<T, false>(p, c, sm, ring, rs, &tmap, sm.cd[0], &sm.cd[1]);
 }
 
 template <typename T>
@@ -913,12 +1122,17 @@ int hemv_upper(cudaStream_t s, int n, const T* A, int64_t lda, const T* x, T* y)
   int64_t ldp;
   size_t pe = partial_elems<T>(n, ldp);
   const int npad = ((n + 63) & ~63) + 64;
-  void* scr = ctx_scratch((2 * pe + npad) * sizeof(T) + 1024);
+  const size_t Tn = (size_t)(n + TB - 1) / TB;
+  const size_t nunits = Tn * (Tn + 1) / 2 + 64;
+  void* scr = ctx_scratch((2 * pe + npad) * sizeof(T) + nunits * sizeof(double) + 4096);
   if (!scr) return -1;
   Arena ar(scr, ctx().scratch_bytes);
   T* Pd = ar.take<T>(pe);
   T* Pt = ar.take<T>(pe);
   T* xpad = ar.take<T>(npad);
+  double* vavunit = ar.take<double>(nunits);
+  unsigned* qctr = ar.take<unsigned>(64);
+  if (!qctr) { set_last_error("hemv: scratch arena too small"); return -1; }
   const int vec_ok = is_cplx<T>::value ? 1 : ((((uintptr_t)A & 15) == 0 && (lda & 1) == 0) ? 1 : 0);
   int tma = (opts().symv_tma != 0 && vec_ok && ((uintptr_t)A & 15) == 0) ? 1 : 0;
   CUtensorMap tmap;
@@ -928,8 +1142,9 @@ int hemv_upper(cudaStream_t s, int n, const T* A, int64_t lda, const T* x, T* y)
   int grid = 0;
   if (panel_grid<T>(grid, tma ? ring_bytes<T>() : 0) != 0) return -1;
   const int C = strip_len(n, grid);
+  EIGB_CUDA_CHECK(cudaMemsetAsync(qctr, 0, sizeof(unsigned), s));
   pad_copy_kernel<T><<<cdiv(npad, 256), 256, 0, s>>>(x, n, xpad, npad);
-  hemv_tiles_kernel<T><<<grid, NTT, tma ? ring_bytes<T>() : 0, s>>>(tmap, A, lda, n, xpad, Pd, Pt, ldp, C, tma, vec_ok);
+  hemv_tiles_kernel<T><<<grid, NTT, tma ? ring_bytes<T>() : 0, s>>>(tmap, A, lda, n, xpad, Pd, Pt, ldp, C, tma, vavunit, qctr);
   EIGB_LAUNCH_CHECK();
   hemv_reduce_kernel<T><<<cdiv(n, 256), 256, 0, s>>>(Pd, Pt, ldp, n, C, y);
   EIGB_LAUNCH_CHECK();
@@ -955,7 +1170,10 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   if (panel_grid<T>(grid, dyn) != 0) return -1;
   int64_t ldp;
   size_t pe = partial_elems<T>(n, ldp);
-  size_t bytes = (2 * pe + (size_t)n * nb + (size_t)n + 256 + (size_t)MAXZU * 2 * NBMAX + 64) * sizeof(T) +
+  const size_t Tnn = (size_t)(n + TB - 1) / TB;
+  const size_t nunits = Tnn * (Tnn + 1) / 2 + 64;
+  size_t bytes = (2 * pe + (size_t)n * nb + (size_t)n + 256 + (size_t)2 * NBMAX + 64) * sizeof(T) +
+                 nunits * sizeof(double) + 4096 +
                  ((size_t)(n / TB + 2) * (size_t)(n / TB + 2) / 2 + 2 * (size_t)(n / TB + 2) + 16) * sizeof(GemmParams<T>) +
                  (size_t)(2 * grid + 64) * sizeof(double) + 4096 + 16 * 256;
   void* scr = ctx_scratch(bytes);
@@ -966,14 +1184,15 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   p.Pd = ar.take<T>(pe); p.Pt = ar.take<T>(pe); p.ldp = ldp;
   p.W = ar.take<T>((size_t)n * nb); p.ldw = n;
   p.xbuf = ar.take<T>((size_t)n + 128);
-  p.zpart = ar.take<T>((size_t)MAXZU * 2 * NBMAX);
+  p.zfin = ar.take<T>((size_t)2 * NBMAX);
   p.alpha_slot = ar.take<T>(16);
+  p.scale_slot = ar.take<T>(16);
   p.npart = ar.take<double>(grid);
-  p.vavpart = ar.take<double>(grid);
-  p.barrier = ar.take<unsigned>(64);
+  p.vavunit = ar.take<double>(nunits);
+  p.barrier = ar.take<unsigned>(64 + NBMAX);      // barrier word + the per-column tile queue heads (one memset)
   p.status = c.d_info;
   if (!p.barrier) { set_last_error("hetrd: scratch arena too small"); return -1; }
-  p.vec_ok = vec_ok;
+  p.qctr = p.barrier + 64;
   p.use_tma = use_tma;
   p.trace = nullptr;
   MgConfig& M = mg();
@@ -993,8 +1212,8 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     if (!GP) { set_last_error("hetrd: scratch arena too small (multi-GPU)"); return -1; }
   }
   if (opts().trd_trace) {
-    if (cudaMalloc(&p.trace, (size_t)n * 5 * sizeof(unsigned long long)) != cudaSuccess) p.trace = nullptr;
-    else cudaMemsetAsync(p.trace, 0, (size_t)n * 5 * sizeof(unsigned long long), s);
+    if (cudaMalloc(&p.trace, (size_t)n * TRSLOTS * sizeof(unsigned long long)) != cudaSuccess) p.trace = nullptr;
+    else cudaMemsetAsync(p.trace, 0, (size_t)n * TRSLOTS * sizeof(unsigned long long), s);
   }
   EIGB_CUDA_CHECK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
   const bool coop = opts().trd_coop != 0;
@@ -1048,8 +1267,8 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
       if (M.hook) M.hook(p.i0, nbp, (p.i0 / TB) % M.P);
     }
     prof_begin(PROF_PANEL, s);
+    EIGB_CUDA_CHECK(cudaMemsetAsync(p.barrier, 0, (64 + NBMAX) * sizeof(unsigned), s));
     if (coop) {
-      EIGB_CUDA_CHECK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), s));
       void* args[] = {&tmap, &p};
       void* kfn = (p.P > 1) ? (void*)panel_coop_kernel<T, true> : (void*)panel_coop_kernel<T, false>;
       EIGB_CUDA_CHECK(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(NTT), args, dyn, s));
@@ -1085,8 +1304,8 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   EIGB_CUDA_CHECK(cudaMemcpyAsync(&st, p.status, sizeof(int), cudaMemcpyDeviceToHost, s));
   EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
   if (p.trace) {
-    trace_store().resize((size_t)n * 5);
-    cudaMemcpy(trace_store().data(), p.trace, (size_t)n * 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    trace_store().resize((size_t)n * TRSLOTS);
+    cudaMemcpy(trace_store().data(), p.trace, (size_t)n * TRSLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(p.trace);
   }
   if (st != 0) { set_last_error("hetrd: device status %d (grid barrier watchdog)", st); return -1; }

@@ -51,8 +51,9 @@ int eigb200_prof_enable(int on);
 int eigb200_prof_reset(void);
 int eigb200_prof_collect(double* ms, int* cnt, long long* launches);
 
-/* profiling aid: with option "trd_trace"=1 the tridiagonalization records 5 globaltimer stamps (ns) per column
- * (phase A start/end, after barrier, phase B end, after barrier); read them back here. Returns the count. */
+/* profiling aid: with option "trd_trace"=1 the tridiagonalization records 16 globaltimer stamps (ns) per column
+ * (slots 0-4: phase A start/end, after barrier, phase B end, after barrier; 5-13: finer steps inside the phases,
+ * see tools/trace_hetrd.py); read them back here. Returns the count. */
 long long eigb200_trace_read(unsigned long long* out, long long max_count);
 
 /* ---- generalized drivers (the drop-in entry points) ------------------------------------------------ */
