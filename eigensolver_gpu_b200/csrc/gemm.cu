@@ -5,13 +5,23 @@ namespace eigb200 {
 
 namespace {
 
-constexpr int BKT = 16;      // k-tile
-constexpr int STAGES = 3;    // cp.async ring depth
 constexpr int KPAD = 4;      // K-major smem row = BKT + 4 elements (conflict-free fragment reads)
+// Two 8-warp CTAs per SM (<= 128 registers per thread): while one CTA waits at its k-tile barrier, runs its
+// prologue or its epilogue, the other one keeps the DMMA pipe busy.  The cp.async ring gets as many stages as fit
+// in half of the SM's shared memory (2..4).
+constexpr int SMEM_PER_CTA = 115712;
 
 template <typename T> struct Cfg;
-template <> struct Cfg<double>  { static constexpr int BM = 128, BN = 128, WGM = 4, WGN = 4, PAD = 4; };
-template <> struct Cfg<double2> { static constexpr int BM = 128, BN = 64,  WGM = 4, WGN = 4, PAD = 2; };
+template <> struct Cfg<double>  { static constexpr int BM = 128, BN = 64, WGM = 4, WGN = 2, PAD = 4, BKT = 16; };
+template <> struct Cfg<double2> { static constexpr int BM = 64,  BN = 64, WGM = 2, WGN = 4, PAD = 2, BKT = 16; };
+template <typename T, bool AK, bool BK> __host__ __device__ constexpr int stage_elems_() {
+  using C_ = Cfg<T>;
+  return (AK ? C_::BM * (C_::BKT + KPAD) : C_::BKT * (C_::BM + C_::PAD)) + (BK ? C_::BN * (C_::BKT + KPAD) : C_::BKT * (C_::BN + C_::PAD));
+}
+template <typename T, bool AK, bool BK> __host__ __device__ constexpr int num_stages_() {
+  constexpr int n = SMEM_PER_CTA / (stage_elems_<T, AK, BK>() * (int)sizeof(T));
+  return n > 4 ? 4 : (n < 2 ? 2 : n);
+}
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -34,7 +44,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 //  KMAJ=false: global element (x, k) at G[x + k*ld]  -> smem S[k*(EXT+PAD) + x]
 //  KMAJ=true : global element (x, k) at G[k + x*ld]  -> smem S[x*(BKT+KPAD) + k]
 // CH = elements per cp.async chunk (16 bytes when CH*sizeof(T)==16, else 8).
-template <typename T, bool KMAJ, int EXT, int PAD, int CH, int NT>
+template <typename T, bool KMAJ, int EXT, int PAD, int CH, int NT, int BKT>
 __device__ __forceinline__ void load_tile(T* S, const T* __restrict__ G, int64_t ld, int x0, int k0, int X, int K,
                                           int tid) {
   constexpr int CB = CH * (int)sizeof(T);
@@ -64,9 +74,9 @@ __device__ __forceinline__ void load_tile(T* S, const T* __restrict__ G, int64_t
 }
 
 template <typename T, bool AK, bool BK, int CH>
-__global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(GemmParams<T> pv, const GemmParams<T>* __restrict__ dev) {
+__global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32, 2) gemm_kernel(GemmParams<T> pv, const GemmParams<T>* __restrict__ dev) {
   using C_ = Cfg<T>;
-  constexpr int BM = C_::BM, BN = C_::BN, WGM = C_::WGM, WGN = C_::WGN, PAD = C_::PAD;
+  constexpr int BM = C_::BM, BN = C_::BN, WGM = C_::WGM, WGN = C_::WGN, PAD = C_::PAD, BKT = C_::BKT;
   constexpr int NT = WGM * WGN * 32;
   constexpr int WTM = BM / WGM, WTN = BN / WGN, MI = WTM / 8, NI = WTN / 8;
   constexpr int A_ELEMS = AK ? BM * (BKT + KPAD) : BKT * (BM + PAD);
@@ -74,6 +84,7 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(Ge
   constexpr int LDA_S = AK ? (BKT + KPAD) : (BM + PAD);
   constexpr int LDB_S = BK ? (BKT + KPAD) : (BN + PAD);
   constexpr bool CPLX = is_cplx<T>::value;
+  constexpr int STAGES = num_stages_<T, AK, BK>();
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
@@ -97,8 +108,8 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(Ge
       int k0 = (kt - (seg ? KT0 : 0)) * BKT;
       T* As = smem + (kt % STAGES) * (A_ELEMS + B_ELEMS);
       T* Bs = As + A_ELEMS;
-      load_tile<T, AK, BM, PAD, CH, NT>(As, p.A[seg], p.lda[seg], m0, k0, p.M, p.K[seg], tid);
-      load_tile<T, BK, BN, PAD, CH, NT>(Bs, p.B[seg], p.ldb[seg], n0, k0, p.N, p.K[seg], tid);
+      load_tile<T, AK, BM, PAD, CH, NT, BKT>(As, p.A[seg], p.lda[seg], m0, k0, p.M, p.K[seg], tid);
+      load_tile<T, BK, BN, PAD, CH, NT, BKT>(Bs, p.B[seg], p.ldb[seg], n0, k0, p.N, p.K[seg], tid);
     }
     cp_async_commit();
   };
@@ -113,6 +124,16 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(Ge
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+  if (p.beta != 0.0 && p.colmap == nullptr) {
+    // the epilogue reads the C tile: pull it into L2 now (128-byte lines, column by column)
+    constexpr int LPC = BM * (int)sizeof(T) / 128;          // lines per tile column
+    for (int id = tid; id < LPC * BN; id += NT) {
+      const int cn = n0 + id / LPC, gm = m0 + (id % LPC) * (128 / (int)sizeof(T));
+      if (cn < p.N && gm < p.M && !(p.mode == 1 && gm > cn + p.diag_off))
+        asm volatile("prefetch.global.L2 [%0];\n" :: "l"(p.C + gm + (int64_t)cn * p.ldc));
+    }
+  }
 
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<STAGES - 2>();
@@ -169,30 +190,43 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(Ge
   }
   cp_async_wait<0>();
 
-  // epilogue: C = alpha*acc + beta*C
+  // epilogue: C = alpha*acc + beta*C.  All loads of a row group are issued before the first store: a store
+  // followed by a load of another C element cannot be reordered by the compiler, and one DRAM round trip per
+  // element (32 of them in a row) used to cost more than the main loop of a K = 64 update.
   const double alpha = p.alpha, beta = p.beta;
+  const bool rd = beta != 0.0;
 #pragma unroll
   for (int i = 0; i < MI; ++i) {
     const int gm = m0 + wm0 + i * 8 + g;
-    if (gm >= p.M) continue;
+    T old[NI][2];
+    T* cps[NI][2];
+    bool ok[NI][2];
 #pragma unroll
     for (int j = 0; j < NI; ++j) {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int gn = n0 + wn0 + j * 8 + 2 * t + r;
-        if (gn >= p.N) continue;
-        if (p.mode == 1 && gm > gn + p.diag_off) continue;
-        const int cn = p.colmap ? p.colmap[gn] : gn;
-        T* cp = p.C + gm + (int64_t)cn * p.ldc;
+        ok[j][r] = gm < p.M && gn < p.N && !(p.mode == 1 && gm > gn + p.diag_off);
+        const int cn = (ok[j][r] && p.colmap) ? p.colmap[gn] : gn;
+        cps[j][r] = p.C + gm + (int64_t)cn * p.ldc;
+        old[j][r] = (ok[j][r] && rd) ? *cps[j][r] : zero_<T>();
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (!ok[j][r]) continue;
         if constexpr (!CPLX) {
           double v = alpha * acc[i][j][r];
-          if (beta != 0.0) v += beta * (*cp);
-          *cp = v;
+          if (rd) v += beta * old[j][r];
+          *cps[j][r] = v;
         } else {
           double2 v = mkz(alpha * acc[i][j][r], alpha * acc[i][j][2 + r]);
-          if (beta != 0.0) { double2 o = *cp; v.x += beta * o.x; v.y += beta * o.y; }
+          if (rd) { v.x += beta * old[j][r].x; v.y += beta * old[j][r].y; }
+          const int gn = n0 + wn0 + j * 8 + 2 * t + r;
           if (p.real_diag && gm == gn + p.diag_off) v.y = 0.0;
-          *cp = v;
+          *cps[j][r] = v;
         }
       }
     }
@@ -202,9 +236,10 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32) gemm_kernel(Ge
 template <typename T, bool AK, bool BK, int CH>
 int launch_one(cudaStream_t s, const GemmParams<T>& p, const GemmParams<T>* dev, int batch, int maxM, int maxN) {
   using C_ = Cfg<T>;
+  constexpr int BKT = C_::BKT;
   constexpr int A_ELEMS = AK ? C_::BM * (BKT + KPAD) : BKT * (C_::BM + C_::PAD);
   constexpr int B_ELEMS = BK ? C_::BN * (BKT + KPAD) : BKT * (C_::BN + C_::PAD);
-  constexpr int SMEM = STAGES * (A_ELEMS + B_ELEMS) * (int)sizeof(T);
+  constexpr int SMEM = num_stages_<T, AK, BK>() * (A_ELEMS + B_ELEMS) * (int)sizeof(T);
   static bool attr_set = false;
   auto kern = gemm_kernel<T, AK, BK, CH>;
   if (!attr_set) {

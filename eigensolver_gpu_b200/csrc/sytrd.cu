@@ -69,6 +69,8 @@ struct TrdP {
   unsigned* qctr;              // [NBMAX] tile-unit queue heads, one per panel column (zeroed per panel)
   int* status;
   int use_tma;                 // tiles staged through the TMA ring (needs 16-byte aligned columns)
+  int upc;                     // target number of tile units per CTA (strip length heuristic)
+  int npf;                     // tiles each CTA prefetches into L2 during phase A (0: off)
   unsigned long long* trace;   // optional: TRSLOTS globaltimer stamps per column (CTA 0), profiling aid
   // multi-GPU (1-D block-cyclic distribution of the 64-wide tile columns of the trailing matrix over P ranks)
   int rank, P;                 // P == 1: single GPU
@@ -160,6 +162,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
                :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n"
+               :: "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;\n" :: "n"(NT) : "memory"); }
 
 // ---- grid barrier (monotonic counter, watchdog-protected) --------------------------------------------
@@ -194,10 +200,10 @@ __device__ __forceinline__ T block_sum(T v, T* red /* >= NWT entries */) {
   return s;
 }
 
-// tiles per strip chunk for an order-n product on G CTAs: aim at >= 6 units per CTA, at most 8 tiles per unit
-__host__ __device__ __forceinline__ int strip_len(int n, int G, int P = 1) {
+// tiles per strip chunk for an order-n product on G CTAs: aim at >= upc units per CTA, at most 8 tiles per unit
+__host__ __device__ __forceinline__ int strip_len(int n, int G, int P, int upc) {
   const int Tn = (n + TB - 1) / TB;
-  int c = (Tn * (Tn - 1) / 2) / (6 * G * P);
+  int c = (Tn * (Tn - 1) / 2) / (upc * G * P);
   if (c < 1) c = 1;
   if (c > 8) c = 8;
   while ((Tn - 1) / c > MAXBANDS) ++c;
@@ -208,11 +214,11 @@ __host__ __device__ __forceinline__ int strip_len(int n, int G, int P = 1) {
 // the phase A that follows (c-1) and is derived one column ahead by a single thread that would otherwise idle
 // (the producer warp, after its last tile): integer divisions and square roots cost ~25 dependent instructions
 // each, and 17 warps repeating them on the critical path of every column was a measurable part of it.
-__device__ void compute_desc(ColDesc& d, int j, int G, int P) {
+__device__ void compute_desc(ColDesc& d, int j, int G, int P, int upc) {
   d.j = j;
   if (j <= 0) { d.Tn = 0; d.C = 1; d.rcpC = 65536; d.KB = 0; d.NF = 0; d.total = 0; d.R = 0; d.ndj = 0; d.nsj = 0; return; }
   const int Tn = (j + TB - 1) / TB;
-  const int C = strip_len(j, G, P);
+  const int C = strip_len(j, G, P, upc);
   d.Tn = Tn; d.C = C; d.rcpC = (65536 + C - 1) / C;
   d.KB = (Tn - 1) / C;
   d.NF = d.KB * Tn - C * (d.KB * (d.KB + 1) / 2);
@@ -389,7 +395,7 @@ template <typename T, class XR>
 __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc,
                            XR xfix, T* Pd, T* Pt, int64_t ldp, double* vavunit, unsigned* qctr, int cta, int G, bool tma,
                            T* ring, uint64_t* full, uint64_t* empty, TileMeta* meta, RingState& rs, EngineSmem<T>& es,
-                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc) {
+                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc, int upc) {
   constexpr int S = RingCfg<T>::STAGES, NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int st = rs.stage;
@@ -431,7 +437,7 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
       unit = __shfl_sync(0xffffffffu, nu, 0);
     }
     // idle from here on: derive the next product's descriptor while the consumers drain the ring
-    if (lane == 0 && next_cd != nullptr) compute_desc(*next_cd, jnext, G, Pdesc);
+    if (lane == 0 && next_cd != nullptr) compute_desc(*next_cd, jnext, G, Pdesc, upc);
   } else {
     // ===================== consumer warps =====================
     const int r4 = 4 * warp;
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(NTT, 1) hemv_tiles_kernel(const __grid_constan
   auto xfix = [n](int r, T raw) -> T { return r < n ? raw : zero_<T>(); };
   const UnitMap um = engine_prepare<T>(n, C, 0, 1, es);
   engine_run<T>(um, A, lda, n, xpad, xfix, Pd, Pt, ldp, vavunit, qctr, blockIdx.x, gridDim.x, tma != 0, ring, full, empty,
-                meta, rs, es, &tmap, nullptr, 0, 1);
+                meta, rs, es, &tmap, nullptr, 0, 1, 6);
 }
 template <typename T>
 __global__ void hemv_reduce_kernel(const T* Pd, const T* Pt, int64_t ldp, int n, int C, T* y) {
@@ -645,7 +651,8 @@ __global__ void pad_copy_kernel(const T* x, int n, T* xpad, int npad) {
 //     and W, the slots of row j, tau, scale -- and derives rho, alpha', W(j, c+1) while the workers run their
 //     V/W loop; the results travel through shared memory.
 template <typename T, bool MG>
-__device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc& cd) {
+__device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc& cd, const ColDesc& cdn,
+                        const CUtensorMap* tmap) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
   const int nbp = p.nbp;
@@ -762,6 +769,26 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
         __syncthreads();                          // (#1)
       }
       __syncthreads();                            // (#2)
+      if (round == 0 && tmap != nullptr && p.npf > 0 && c >= 0 && !mg && cdn.j > 0 &&
+          (int64_t)cdn.Tn * (cdn.Tn + 1) * (int64_t)(TB * TB * sizeof(T) / 2) > (int64_t)(96 << 20)) {
+        // HBM idles during this phase, the barrier and the Householder scalars: pull the first tiles this CTA
+        // will be handed in the coming product into L2 (they were the first ones used for the previous column,
+        // i.e. the ones most certainly evicted since)
+        constexpr int NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
+        UnitMap um;
+        um.Tn = cdn.Tn; um.C = cdn.C; um.rcpC = cdn.rcpC; um.rank = 0; um.P = 1; um.TnO = cdn.Tn; um.KB = cdn.KB;
+        um.NF = cdn.NF; um.total = cdn.total; um.bstart = nullptr;
+        int left = p.npf;
+        for (int unit = cta; unit < um.total && left > 0; unit += G) {
+          int J, I0, I1; bool hd;
+          um.decode(unit, J, I0, I1, hd);
+          const int ntile = (I1 - I0) + (hd ? 1 : 0);
+          for (int t = 0; t < ntile && left > 0; ++t, --left) {
+            const int I = (hd && t == ntile - 1) ? J : I0 + t;
+            if (lane < NBOX) tma_prefetch_2d(tmap, (I * TB) * DPE + lane * 16, J * TB);
+          }
+        }
+      }
       continue;
     }
     // ===================== worker warps =====================
@@ -791,13 +818,12 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
           {
             const T* ptr = p.Pd + (int64_t)(I + 1 + sub) * p.ldp + r;
             int cnt = nd > sub ? (nd - sub + WPG - 1) >> wpgs : 0;
-            for (; cnt > 0; cnt -= 4) {
-              const T v0 = ldcg_(ptr);
-              const T v1 = cnt > 1 ? ldcg_(ptr + step) : zero_<T>();
-              const T v2 = cnt > 2 ? ldcg_(ptr + 2 * step) : zero_<T>();
-              const T v3 = cnt > 3 ? ldcg_(ptr + 3 * step) : zero_<T>();
-              ptr += 4 * step;
-              wr = add_(wr, add_(add_(v0, v1), add_(v2, v3)));
+            for (; cnt > 0; cnt -= 8) {
+              T v[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = cnt > k ? ldcg_(ptr + k * step) : zero_<T>();
+              ptr += 8 * step;
+              wr = add_(wr, add_(add_(add_(v[0], v[1]), add_(v[2], v[3])), add_(add_(v[4], v[5]), add_(v[6], v[7]))));
             }
           }
           {
@@ -981,7 +1007,7 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
   tstamp(p, c, 13);
   // -- the tile engine: w_raw partials and v^H A v
   engine_run<T>(um, p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, p.vavunit, p.qctr + c, cta, G, p.use_tma != 0, ring,
-                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn);
+                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn, p.upc);
   return um.total;
 }
 
@@ -993,7 +1019,7 @@ __device__ void phase_c(const TrdP<T>& p, int c, PanelSmem<T>& sm, int total_uni
   const int G = gridDim.x, cta = blockIdx.x;
   const int j = p.i0 + c;
   if (j <= 0) return;
-  const int Tn = (j + TB - 1) / TB, C = strip_len(j, G, p.P);
+  const int Tn = (j + TB - 1) / TB, C = strip_len(j, G, p.P, p.upc);
   const unsigned par = (unsigned)(col_seq(p, c) & 1ull);
   // groups of 32 rows are dealt to the CTAs; AW warps split the partial-sum slots of a group (L2-latency bound),
   // warp 0 combines and pushes the 32 values to every rank
@@ -1041,13 +1067,13 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
   T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
   RingState rs;
   const int Pn = MG ? p.P : 1;
-  if (threadIdx.x == NT) compute_desc(sm.cd[(p.nbp - 1) & 1], p.i0 + p.nbp - 1, gridDim.x, Pn);
+  if (threadIdx.x == NT) compute_desc(sm.cd[(p.nbp - 1) & 1], p.i0 + p.nbp - 1, gridDim.x, Pn, p.upc);
   ring_init(sm.full, sm.empty, RingCfg<T>::STAGES, rs);      // (CTA barrier inside)
   unsigned target = 0;
   auto stamp = [&](int c, int k) { tstamp(p, c, k); };
   for (int c = p.nbp - 1; c >= -1; --c) {
     if (c >= 0) stamp(c, 0);
-    phase_a<T, MG>(p, c, sm, sm.cd[(c + 1) & 1]);
+    phase_a<T, MG>(p, c, sm, sm.cd[(c + 1) & 1], sm.cd[c & 1], &tmap);
     if (c < 0) break;
     stamp(c, 1);
     target += gridDim.x;
@@ -1072,9 +1098,9 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
 template <typename T>
 __global__ void __launch_bounds__(NTT, 1) phase_a_kernel(TrdP<T> p, int c) {
   __shared__ PanelSmem<T> sm;
-  if (threadIdx.x == 0) compute_desc(sm.cd[0], p.i0 + c + 1, gridDim.x, 1);
+  if (threadIdx.x == 0) compute_desc(sm.cd[0], p.i0 + c + 1, gridDim.x, 1, p.upc);
   __syncthreads();
-  phase_a<T, false>(p, c, sm, sm.cd[0]);
+  phase_a<T, false>(p, c, sm, sm.cd[0], sm.cd[0], nullptr);
   __syncthreads();
   if (threadIdx.x == 0 && c >= 0) store_npart(p, sm);
 }
@@ -1084,7 +1110,7 @@ __global__ void __launch_bounds__(NTT, 1) phase_b_kernel(const __grid_constant__
   __shared__ PanelSmem<T> sm;
   T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
   RingState rs;
-  if (threadIdx.x == NT) compute_desc(sm.cd[0], p.i0 + c, gridDim.x, 1);
+  if (threadIdx.x == NT) compute_desc(sm.cd[0], p.i0 + c, gridDim.x, 1, p.upc);
   ring_init(sm.full, sm.empty, RingCfg<T>::STAGES, rs);
   phase_b<T, false>(p, c, sm, ring, rs, &tmap, sm.cd[0], &sm.cd[1]);
 }
@@ -1141,7 +1167,7 @@ int hemv_upper(cudaStream_t s, int n, const T* A, int64_t lda, const T* x, T* y)
     tma = 0;
   int grid = 0;
   if (panel_grid<T>(grid, tma ? ring_bytes<T>() : 0) != 0) return -1;
-  const int C = strip_len(n, grid);
+  const int C = strip_len(n, grid, 1, opts().trd_upc);
   EIGB_CUDA_CHECK(cudaMemsetAsync(qctr, 0, sizeof(unsigned), s));
   pad_copy_kernel<T><<<cdiv(npad, 256), 256, 0, s>>>(x, n, xpad, npad);
   hemv_tiles_kernel<T><<<grid, NTT, tma ? ring_bytes<T>() : 0, s>>>(tmap, A, lda, n, xpad, Pd, Pt, ldp, C, tma, vavunit, qctr);
@@ -1194,6 +1220,8 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   if (!p.barrier) { set_last_error("hetrd: scratch arena too small"); return -1; }
   p.qctr = p.barrier + 64;
   p.use_tma = use_tma;
+  p.upc = opts().trd_upc;
+  p.npf = use_tma ? (opts().trd_prefetch >= 0 ? opts().trd_prefetch : (is_cplx<T>::value ? 4 : 8)) : 0;
   p.trace = nullptr;
   MgConfig& M = mg();
   p.rank = 0; p.P = 1;
