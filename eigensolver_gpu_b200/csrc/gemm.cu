@@ -289,6 +289,10 @@ int gemm_launch(cudaStream_t s, bool AK, bool BK, const GemmParams<T>& p, const 
   return -1;
 }
 
+template <typename T> void gemm_tile_dims(int& bm, int& bn) { bm = Cfg<T>::BM; bn = Cfg<T>::BN; }
+template void gemm_tile_dims<double>(int&, int&);
+template void gemm_tile_dims<double2>(int&, int&);
+
 template <typename T>
 int gemm(cudaStream_t s, char ta, char tb, int M, int N, int K, double alpha, const T* A, int64_t lda, const T* B,
          int64_t ldb, double beta, T* C, int64_t ldc, int mode) {

@@ -35,6 +35,9 @@ template <typename T>
 int gemm_launch(cudaStream_t s, bool AK, bool BK, const GemmParams<T>& p, const GemmParams<T>* dev_params = nullptr,
                 int batch = 1, int maxM = 0, int maxN = 0);
 
+// CTA tile of the kernel for element type T (callers that need to know how many CTAs a shape produces)
+template <typename T> void gemm_tile_dims(int& bm, int& bn);
+
 // BLAS-like convenience: C = alpha*op(A)*op(B) + beta*C
 template <typename T>
 int gemm(cudaStream_t s, char ta, char tb, int M, int N, int K, double alpha, const T* A, int64_t lda, const T* B,

@@ -73,12 +73,35 @@ __global__ void __launch_bounds__(256) bt_finish_t_kernel(T* Tm_all, const T* __
   }
 }
 
+// X(0:rows, 0:cols) = sum over the S slices (fixed order: deterministic) of a split-K product
+template <typename T>
+__global__ void bt_sum_slices_kernel(const T* __restrict__ Xs, int S, int64_t slice, T* X, int rows, int cols, int ld) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (r >= rows || c >= cols) return;
+  const int64_t o = r + (int64_t)c * ld;
+  T acc = Xs[o];
+  for (int q = 1; q < S; ++q) acc = add_(acc, Xs[o + q * slice]);
+  X[o] = acc;
+}
+
+// V^H Z has only ib rows: with few eigenvector columns it does not produce enough CTAs to fill the GPU, so its
+// K range (the block height) is split over up to 16 CTA groups whose partial products are summed afterwards.
+int bt_splits(int m, int ib, int esize) {
+  int bm, bn;
+  if (esize == 16) gemm_tile_dims<double2>(bm, bn); else gemm_tile_dims<double>(bm, bn);
+  const int ntile = ((ib + bm - 1) / bm) * ((m + bn - 1) / bn);
+  int S = 296 / (ntile > 0 ? ntile : 1);
+  return S < 1 ? 1 : (S > 16 ? 16 : S);
+}
+
 }  // namespace
 
 size_t ormtr_scratch_bytes(int n, int m, int esize) {
   int ib = opts().bt_nb < BTMAX ? opts().bt_nb : BTMAX;
   size_t nblk = (size_t)(n > 1 ? (n - 2) / ib + 1 : 1);
-  return ((size_t)n * n + nblk * BTMAX * BTMAX + 2 * (size_t)BTMAX * m) * esize + nblk * 256 + 8 * 256;
+  const size_t S = (size_t)bt_splits(m, ib, esize);
+  return ((size_t)n * n + nblk * BTMAX * BTMAX + (2 + (S > 1 ? S : 0)) * (size_t)BTMAX * m) * esize +
+         (nblk * (S + 1) + 8) * 256;
 }
 
 // Z(0:n, 0:m) <- Q Z.  A holds the reflectors (v_j in A(0:j, j+1), unit element explicit or not -- it is
@@ -98,8 +121,11 @@ int ormtr_upper(cudaStream_t s, int n, int m, const T* A, int64_t lda, const T* 
   T* Tm = ar.take<T>((size_t)nblk * BTMAX * BTMAX);
   T* X1 = ar.take<T>((size_t)BTMAX * m);
   T* X2 = ar.take<T>((size_t)BTMAX * m);
+  const int S = bt_splits(m, ib, (int)sizeof(T));
+  T* X1s = S > 1 ? ar.take<T>((size_t)S * BTMAX * m) : nullptr;
   GemmParams<T>* GP = ar.take<GemmParams<T>>(nblk);
-  if (!GP) { set_last_error("ormtr: scratch arena exhausted"); return -1; }
+  GemmParams<T>* GPS = S > 1 ? ar.take<GemmParams<T>>((size_t)nblk * S) : nullptr;
+  if (!GP || (S > 1 && (!X1s || !GPS))) { set_last_error("ormtr: scratch arena exhausted"); return -1; }
   bt_prepare_v_kernel<T><<<dim3(cdiv(n, 256), nref), 256, 0, s>>>(A, lda, n, ib, VW, ldv);
   EIGB_LAUNCH_CHECK();
   // T0 = V^H V for every block (small outputs, long K): ONE batched launch, parameter blocks read from device memory
@@ -122,11 +148,40 @@ int ormtr_upper(cudaStream_t s, int n, int m, const T* A, int64_t lda, const T* 
   }
   bt_finish_t_kernel<T><<<nblk, 256, 0, s>>>(Tm, tau, n, ib);
   EIGB_LAUNCH_CHECK();
+  std::vector<int> nsplit(nblk, 1);
+  if (S > 1) {
+    // split-K parameter blocks of X1 = V^H Z for every reflector block, uploaded once
+    std::vector<GemmParams<T>> hp((size_t)nblk * S);
+    for (int b = 0; b < nblk; ++b) {
+      const int j0 = b * ib, ibb = (nref - j0 < ib) ? nref - j0 : ib, mi = j0 + ibb;
+      int Sb = mi / 256; Sb = Sb < 1 ? 1 : (Sb > S ? S : Sb);
+      const int kc = (((mi + Sb - 1) / Sb) + 15) & ~15;
+      Sb = (mi + kc - 1) / kc;
+      nsplit[b] = Sb;
+      for (int q = 0; q < Sb; ++q) {
+        GemmParams<T>& g = hp[(size_t)b * S + q];
+        memset(&g, 0, sizeof(g));
+        const int kbeg = q * kc, kk = (mi - kbeg < kc) ? mi - kbeg : kc;
+        g.M = ibb; g.N = m; g.nseg = 1;
+        g.A[0] = VW + (int64_t)j0 * ldv + kbeg; g.lda[0] = ldv; g.B[0] = Z + kbeg; g.ldb[0] = ldz; g.K[0] = kk;
+        g.A[1] = g.A[0]; g.B[1] = g.B[0]; g.lda[1] = ldv; g.ldb[1] = ldz; g.K[1] = 0;
+        g.sa[0] = g.sa[1] = -1.0; g.sb[0] = g.sb[1] = 1.0;     // op(A) = V^H
+        g.C = X1s + (int64_t)q * BTMAX * m; g.ldc = BTMAX;
+        g.alpha = 1.0; g.beta = 0.0; g.mode = 0; g.real_diag = 0; g.colmap = nullptr;
+      }
+    }
+    EIGB_CUDA_CHECK(cudaMemcpyAsync(GPS, hp.data(), sizeof(GemmParams<T>) * hp.size(), cudaMemcpyHostToDevice, s));
+  }
   // apply the blocks in ascending order: Z <- Z - V (T (V^H Z))
   for (int b = 0; b < nblk; ++b) {
     const int j0 = b * ib, ibb = (nref - j0 < ib) ? nref - j0 : ib, mi = j0 + ibb;
     const T* V = VW + (int64_t)j0 * ldv;
-    if (gemm<T>(s, 'C', 'N', ibb, m, mi, 1.0, V, ldv, Z, ldz, 0.0, X1, BTMAX) != 0) return -1;
+    if (nsplit[b] > 1) {
+      GemmParams<T> dummy{};
+      if (gemm_launch<T>(s, true, true, dummy, GPS + (size_t)b * S, nsplit[b], ibb, m) != 0) return -1;
+      bt_sum_slices_kernel<T><<<dim3(cdiv(ibb, 128), m), 128, 0, s>>>(X1s, nsplit[b], (int64_t)BTMAX * m, X1, ibb, m, BTMAX);
+      EIGB_LAUNCH_CHECK();
+    } else if (gemm<T>(s, 'C', 'N', ibb, m, mi, 1.0, V, ldv, Z, ldz, 0.0, X1, BTMAX) != 0) return -1;
     if (gemm<T>(s, 'N', 'N', ibb, m, ibb, 1.0, Tm + (int64_t)b * BTMAX * BTMAX, BTMAX, X1, BTMAX, 0.0, X2, BTMAX) != 0)
       return -1;
     if (gemm<T>(s, 'N', 'N', mi, m, ibb, -1.0, V, ldv, X2, BTMAX, 1.0, Z, ldz) != 0) return -1;

@@ -29,54 +29,63 @@ template <> __device__ __forceinline__ double2 recip_<double2>(double2 a) {
   r = a.x / a.y; den = a.y + a.x * r; return mkz(r / den, -1.0 / den);
 }
 
+// Dinv[b] = inverse of the b-th 64x64 diagonal block of the upper-triangular U.  grid (blocks, 8), 256 threads:
+// one warp per column j of the inverse, lanes = rows (lane, lane+32), column-oriented back substitution
+// (x_l final -> rows i < l get  acc_i -= u(i,l) x_l): 64 dependent steps of one shuffle + two FMAs per lane
+// instead of one thread walking an O(j^2) dependent chain.  b0 = first block handled by blockIdx.x == 0.
 template <typename T>
-__device__ void tri_inverse_smem(const T* s, T* inv, int nb) {
-  const int j = threadIdx.x;
-  if (j < nb) {
-    for (int i = nb - 1; i > j; --i) inv[i + j * (NB + 1)] = zero_<T>();
-    inv[j + j * (NB + 1)] = recip_<T>(s[j + j * (NB + 1)]);
-    for (int i = j - 1; i >= 0; --i) {
-      T acc = zero_<T>();
-      for (int l = i + 1; l <= j; ++l) fma_(acc, s[i + l * (NB + 1)], inv[l + j * (NB + 1)]);
-      inv[i + j * (NB + 1)] = neg_(mul_(acc, recip_<T>(s[i + i * (NB + 1)])));
+__global__ void __launch_bounds__(256) trtri_blocks_kernel(const T* __restrict__ U, int64_t ldu, int n, T* Dinv, int b0) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  T* s = reinterpret_cast<T*>(dyn_smem);            // U block, column-major, ld = NB+1
+  T* rinv = s + NB * (NB + 1);                      // 1 / u_ll
+  const int b = b0 + blockIdx.x, r0 = b * NB, nb = min(NB, n - r0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx & (NB - 1), c = idx >> 6;
+    T v = zero_<T>();
+    if (r < nb && c < nb) { if (r <= c) v = U[(r0 + r) + (int64_t)(r0 + c) * ldu]; }
+    else if (r == c) v = from_real<T>(1.0);         // identity padding of a partial last block
+    s[r + c * (NB + 1)] = v;
+  }
+  __syncthreads();
+  if (tid < NB) rinv[tid] = recip_<T>(s[tid + tid * (NB + 1)]);
+  __syncthreads();
+  const int j = blockIdx.y * 8 + warp;              // column of the inverse
+  T acc0 = zero_<T>(), acc1 = zero_<T>(), x0 = zero_<T>(), x1 = zero_<T>();
+  if (j == lane) acc0 = from_real<T>(1.0);
+  if (j == lane + 32) acc1 = from_real<T>(1.0);
+  for (int l = j; l >= 0; --l) {
+    const T cand = (l >> 5) ? acc1 : acc0;
+    T xl;
+    if constexpr (is_cplx<T>::value) {
+      xl = mkz(__shfl_sync(0xffffffffu, cand.x, l & 31), __shfl_sync(0xffffffffu, cand.y, l & 31));
+    } else {
+      xl = __shfl_sync(0xffffffffu, cand, l & 31);
     }
+    xl = mul_(xl, rinv[l]);
+    if (lane == (l & 31)) { if (l >> 5) x1 = xl; else x0 = xl; }
+    const T* col = s + l * (NB + 1);
+    if (lane < l) acc0 = sub_(acc0, mul_(col[lane], xl));
+    if (lane + 32 < l) acc1 = sub_(acc1, mul_(col[lane + 32], xl));
   }
+  T* out = Dinv + (int64_t)b * NB * NB + (int64_t)j * NB;
+  out[lane] = (lane < nb && j < nb) ? x0 : zero_<T>();
+  out[lane + 32] = (lane + 32 < nb && j < nb) ? x1 : zero_<T>();
 }
 
-// Dinv[b] = inverse of the b-th 64x64 diagonal block of the upper-triangular U (batched over blocks)
+// Cholesky of one 64x64 diagonal block (upper: A = U^H U).  info: first failing pivot (1-based, global index)
+// via CAS on *info (0 = ok).  256 threads: thread (l = tid % 64, q = tid / 64) owns rows q, q+4, ... of column l.
 template <typename T>
-__global__ void __launch_bounds__(NB) trtri_blocks_kernel(const T* __restrict__ U, int64_t ldu, int n, T* Dinv) {
+__global__ void __launch_bounds__(256) potf2_block_kernel(T* A, int64_t lda, int r0, int nb, int* info) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   T* s = reinterpret_cast<T*>(dyn_smem);
-  T* inv = s + NB * (NB + 1);
-  const int b = blockIdx.x, r0 = b * NB, nb = min(NB, n - r0);
-  for (int c = 0; c < nb; ++c) {
-    const int r = threadIdx.x;
-    if (r < nb) s[r + c * (NB + 1)] = (r <= c) ? U[(r0 + r) + (int64_t)(r0 + c) * ldu] : zero_<T>();
-  }
-  __syncthreads();
-  tri_inverse_smem<T>(s, inv, nb);
-  __syncthreads();
-  T* out = Dinv + (int64_t)b * NB * NB;
-  for (int c = 0; c < NB; ++c) {
-    const int r = threadIdx.x;
-    out[r + c * NB] = (r < nb && c < nb) ? inv[r + c * (NB + 1)] : zero_<T>();
-  }
-}
-
-// Cholesky of one 64x64 diagonal block (upper: A = U^H U) + its inverse.  info: first failing pivot (1-based,
-// global index) via atomicMin-style CAS on *info (0 = ok).
-template <typename T>
-__global__ void __launch_bounds__(256) potf2_block_kernel(T* A, int64_t lda, int r0, int nb, T* Dinv, int* info) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  T* s = reinterpret_cast<T*>(dyn_smem);
-  T* inv = s + NB * (NB + 1);
   __shared__ int bad;
   const int tid = threadIdx.x;
+  const int l = tid & (NB - 1), q = tid >> 6;
   if (tid == 0) bad = 0;
-  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-    const int r = idx % nb, c = idx / nb;
-    s[r + c * (NB + 1)] = (r <= c) ? A[(r0 + r) + (int64_t)(r0 + c) * lda] : zero_<T>();
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx & (NB - 1), c = idx >> 6;
+    s[r + c * (NB + 1)] = (r <= c && c < nb) ? A[(r0 + r) + (int64_t)(r0 + c) * lda] : zero_<T>();
   }
   __syncthreads();
   // outer-product Cholesky with ONE barrier per step: row j is used unscaled (a_il -= conj(a_ji) a_jl / a_jj) and the
@@ -84,95 +93,90 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(T* A, int64_t lda, int
   for (int j = 0; j < nb; ++j) {
     const double piv = real_(s[j + j * (NB + 1)]);
     if (!(piv > 0.0)) { if (tid == 0 && bad == 0) bad = r0 + j + 1; }
-    const double ipiv = 1.0 / piv;
-    const int m = nb - j - 1;
-    for (int idx = tid; idx < m * m; idx += blockDim.x) {
-      const int i = j + 1 + idx % m, l = j + 1 + idx / m;
-      if (i <= l) {
+    if (l > j && l < nb) {
+      const T f = scale_(s[j + l * (NB + 1)], 1.0 / piv);
+      for (int i = j + 1 + q; i <= l; i += 4) {
         T t = zero_<T>();
-        fmac_(t, s[j + i * (NB + 1)], s[j + l * (NB + 1)]);
-        s[i + l * (NB + 1)] = sub_(s[i + l * (NB + 1)], scale_(t, ipiv));
+        fmac_(t, s[j + i * (NB + 1)], f);
+        s[i + l * (NB + 1)] = sub_(s[i + l * (NB + 1)], t);
       }
     }
     __syncthreads();
   }
-  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-    const int r = idx % nb, c = idx / nb;
-    if (r < c) {
-      const double rs = 1.0 / sqrt(real_(s[r + r * (NB + 1)]));
-      inv[r + c * (NB + 1)] = scale_(s[r + c * (NB + 1)], rs);     // staged in `inv` (diagonal still needed unscaled)
+  // row r scaled by 1/sqrt(a_rr); diagonal = sqrt(a_rr)
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx & (NB - 1), c = idx >> 6;
+    if (r <= c && c < nb) {
+      const double drr = real_(s[r + r * (NB + 1)]);
+      const T v = (r == c) ? from_real<T>(sqrt(drr)) : scale_(s[r + c * (NB + 1)], 1.0 / sqrt(drr));
+      A[(r0 + r) + (int64_t)(r0 + c) * lda] = v;
     }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-    const int r = idx % nb, c = idx / nb;
-    if (r < c) s[r + c * (NB + 1)] = inv[r + c * (NB + 1)];
-  }
-  __syncthreads();
-  if (tid < nb) s[tid + tid * (NB + 1)] = from_real<T>(sqrt(real_(s[tid + tid * (NB + 1)])));
-  __syncthreads();
-  for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
-    const int r = idx % nb, c = idx / nb;
-    if (r <= c) A[(r0 + r) + (int64_t)(r0 + c) * lda] = s[r + c * (NB + 1)];
-  }
-  tri_inverse_smem<T>(s, inv, nb);
-  __syncthreads();
-  for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-    const int r = idx % NB, c = idx / NB;
-    Dinv[r + c * NB] = (r < nb && c < nb) ? inv[r + c * (NB + 1)] : zero_<T>();
   }
   if (tid == 0 && bad != 0) atomicCAS(info, 0, bad);
 }
 
-// In-place multiply of a 64-row (left) or 64-column (right) panel by a 64x64 block M (or M^H):
-//  LEFT : B(r0:r0+nb, :)  <- op(M) * B(r0:r0+nb, :)      grid.x over column strips of 64
-//  RIGHT: B(:, c0:c0+nb)  <- B(:, c0:c0+nb) * op(M)      grid.x over row strips of 64
-template <typename T, bool LEFT, bool CONJT>
+// In-place multiply of a 64-row (left) or 64-column (right) panel by a 64x64 block M (or M^H), one CTA per strip
+// of SW columns (left) / rows (right) of the panel:
+//  LEFT : B(off:off+nb, :)  <- op(M) * B(off:off+nb, :)
+//  RIGHT: B(:, off:off+nb)  <- B(:, off:off+nb) * op(M)
+// SW = 64 when the panel is long enough to fill the GPU, 16 otherwise (4x the CTAs: one SM needs ~8 us for a
+// 64^3 complex product whatever the instruction mix, FP64 FMA and DMMA peak rates being equal on this part).
+template <typename T, bool LEFT, bool CONJT, int SW>
 __global__ void __launch_bounds__(256) diag_mult_kernel(const T* __restrict__ M, T* B, int64_t ldb, int off, int nb,
                                                         int other_beg, int other_end) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   T* sm = reinterpret_cast<T*>(dyn_smem);
   T* sb = sm + NB * (NB + 1);
+  constexpr int OPT = SW / 4;                       // outputs per thread
+  constexpr int LDB_S = (LEFT ? NB : SW) + 1;       // sb: LEFT 64 x SW, RIGHT SW x 64 (column-major)
   const int tid = threadIdx.x;
-  const int o0 = other_beg + blockIdx.x * NB;
-  const int on = min(NB, other_end - o0);
+  const int o0 = other_beg + blockIdx.x * SW;
+  const int on = min(SW, other_end - o0);
   if (on <= 0) return;
-  for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-    const int r = idx % NB, c = idx / NB;
-    // sm holds op(M): element (r, c)
-    T v = CONJT ? conj_(M[c + r * NB]) : M[r + c * NB];
-    sm[r + c * (NB + 1)] = v;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx & (NB - 1), c = idx >> 6;
+    sm[r + c * (NB + 1)] = CONJT ? conj_(M[c + r * NB]) : M[r + c * NB];     // element (r, c) of op(M)
   }
-  // sb(r, c): LEFT: rows r = panel row, c = strip column; RIGHT: r = strip row, c = panel column
-  for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-    const int r = idx % NB, c = idx / NB;
-    T v = zero_<T>();
-    if (LEFT) { if (r < nb && c < on) v = B[(off + r) + (int64_t)(o0 + c) * ldb]; }
-    else      { if (r < on && c < nb) v = B[(o0 + r) + (int64_t)(off + c) * ldb]; }
-    sb[r + c * (NB + 1)] = v;
-  }
-  __syncthreads();
-  // each thread computes 16 outputs: rows r = tid % 64, columns c = tid/64 + 4*q
-  const int r = tid % NB;
-  T acc[NB / 4];
-#pragma unroll
-  for (int q = 0; q < NB / 4; ++q) acc[q] = zero_<T>();
-  for (int l = 0; l < NB; ++l) {
-    if (LEFT) {
-      const T a = sm[r + l * (NB + 1)];
-#pragma unroll
-      for (int q = 0; q < NB / 4; ++q) fma_(acc[q], a, sb[l + (tid / NB + 4 * q) * (NB + 1)]);
-    } else {
-      const T a = sb[r + l * (NB + 1)];
-#pragma unroll
-      for (int q = 0; q < NB / 4; ++q) fma_(acc[q], a, sm[l + (tid / NB + 4 * q) * (NB + 1)]);
+  if (LEFT) {
+    for (int idx = tid; idx < NB * SW; idx += 256) {
+      const int r = idx & (NB - 1), c = idx >> 6;
+      sb[r + c * LDB_S] = (r < nb && c < on) ? B[(off + r) + (int64_t)(o0 + c) * ldb] : zero_<T>();
+    }
+  } else {
+    for (int idx = tid; idx < NB * SW; idx += 256) {
+      const int r = idx % SW, c = idx / SW;
+      sb[r + c * LDB_S] = (r < on && c < nb) ? B[(o0 + r) + (int64_t)(off + c) * ldb] : zero_<T>();
     }
   }
+  __syncthreads();
+  T acc[OPT];
 #pragma unroll
-  for (int q = 0; q < NB / 4; ++q) {
-    const int c = tid / NB + 4 * q;
-    if (LEFT) { if (r < nb && c < on) B[(off + r) + (int64_t)(o0 + c) * ldb] = acc[q]; }
-    else      { if (r < on && c < nb) B[(o0 + r) + (int64_t)(off + c) * ldb] = acc[q]; }
+  for (int q = 0; q < OPT; ++q) acc[q] = zero_<T>();
+  if (LEFT) {
+    const int r = tid & (NB - 1), cg = tid >> 6;    // columns cg + 4q
+    for (int l = 0; l < NB; ++l) {
+      const T a = sm[r + l * (NB + 1)];
+#pragma unroll
+      for (int q = 0; q < OPT; ++q) fma_(acc[q], a, sb[l + (cg + 4 * q) * LDB_S]);
+    }
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) {
+      const int c = cg + 4 * q;
+      if (r < nb && c < on) B[(off + r) + (int64_t)(o0 + c) * ldb] = acc[q];
+    }
+  } else {
+    constexpr int CG = 256 / SW;                    // column groups; columns cg + CG*q
+    const int r = tid % SW, cg = tid / SW;
+    for (int l = 0; l < NB; ++l) {
+      const T a = sb[r + l * LDB_S];
+#pragma unroll
+      for (int q = 0; q < OPT; ++q) fma_(acc[q], a, sm[l + (cg + CG * q) * (NB + 1)]);
+    }
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) {
+      const int c = cg + CG * q;
+      if (r < on && c < nb) B[(o0 + r) + (int64_t)(off + c) * ldb] = acc[q];
+    }
   }
 }
 
@@ -194,6 +198,7 @@ __global__ void restore_lower_kernel(T* A, int64_t lda, int n, const T* save, in
 }
 
 template <typename T> constexpr size_t blk_smem() { return 2 * (size_t)NB * (NB + 1) * sizeof(T); }
+template <typename T> constexpr size_t tri_smem() { return ((size_t)NB * (NB + 1) + NB) * sizeof(T); }
 
 template <typename K>
 int enable_smem(K kern, size_t bytes) {
@@ -204,11 +209,14 @@ template <typename T>
 int enable_all_smem() {
   static bool done = false;
   if (done) return 0;
-  if (enable_smem(trtri_blocks_kernel<T>, blk_smem<T>()) != 0) return -1;
-  if (enable_smem(potf2_block_kernel<T>, blk_smem<T>()) != 0) return -1;
-  if (enable_smem(diag_mult_kernel<T, true, true>, blk_smem<T>()) != 0) return -1;
-  if (enable_smem(diag_mult_kernel<T, true, false>, blk_smem<T>()) != 0) return -1;
-  if (enable_smem(diag_mult_kernel<T, false, false>, blk_smem<T>()) != 0) return -1;
+  if (enable_smem(trtri_blocks_kernel<T>, tri_smem<T>()) != 0) return -1;
+  if (enable_smem(potf2_block_kernel<T>, tri_smem<T>()) != 0) return -1;
+  if (enable_smem(diag_mult_kernel<T, true, true, 64>, blk_smem<T>()) != 0) return -1;
+  if (enable_smem(diag_mult_kernel<T, true, false, 64>, blk_smem<T>()) != 0) return -1;
+  if (enable_smem(diag_mult_kernel<T, false, false, 64>, blk_smem<T>()) != 0) return -1;
+  if (enable_smem(diag_mult_kernel<T, true, true, 16>, blk_smem<T>()) != 0) return -1;
+  if (enable_smem(diag_mult_kernel<T, true, false, 16>, blk_smem<T>()) != 0) return -1;
+  if (enable_smem(diag_mult_kernel<T, false, false, 16>, blk_smem<T>()) != 0) return -1;
   done = true;
   return 0;
 }
@@ -248,12 +256,21 @@ int trsm_rec(cudaStream_t s, char side, char trans, int lo, int hi, int other, c
   if (hi - lo <= NB) {
     const T* M = Dinv + (int64_t)(lo / NB) * NB * NB;
     const int nb = hi - lo;
-    if (side == 'L' && trans == 'N')
-      diag_mult_kernel<T, true, false><<<cdiv(other, NB), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
-    else if (side == 'L')
-      diag_mult_kernel<T, true, true><<<cdiv(other, NB), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
-    else
-      diag_mult_kernel<T, false, false><<<cdiv(other, NB), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+    if (other >= 120 * NB) {
+      if (side == 'L' && trans == 'N')
+        diag_mult_kernel<T, true, false, 64><<<cdiv(other, 64), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+      else if (side == 'L')
+        diag_mult_kernel<T, true, true, 64><<<cdiv(other, 64), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+      else
+        diag_mult_kernel<T, false, false, 64><<<cdiv(other, 64), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+    } else {
+      if (side == 'L' && trans == 'N')
+        diag_mult_kernel<T, true, false, 16><<<cdiv(other, 16), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+      else if (side == 'L')
+        diag_mult_kernel<T, true, true, 16><<<cdiv(other, 16), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+      else
+        diag_mult_kernel<T, false, false, 16><<<cdiv(other, 16), 256, blk_smem<T>(), s>>>(M, B, ldb, lo, nb, 0, other);
+    }
     EIGB_LAUNCH_CHECK();
     return 0;
   }
@@ -279,7 +296,9 @@ int trsm_rec(cudaStream_t s, char side, char trans, int lo, int hi, int other, c
 template <typename T>
 int potrf_rec(cudaStream_t s, int lo, int hi, T* A, int64_t lda, T* Dinv, int* dinfo) {
   if (hi - lo <= NB) {
-    potf2_block_kernel<T><<<1, 256, blk_smem<T>(), s>>>(A, lda, lo, hi - lo, Dinv + (int64_t)(lo / NB) * NB * NB, dinfo);
+    potf2_block_kernel<T><<<1, 256, tri_smem<T>(), s>>>(A, lda, lo, hi - lo, dinfo);
+    EIGB_LAUNCH_CHECK();
+    trtri_blocks_kernel<T><<<dim3(1, 8), 256, tri_smem<T>(), s>>>(A, lda, hi, Dinv, lo / NB);
     EIGB_LAUNCH_CHECK();
     return 0;
   }
@@ -327,7 +346,7 @@ int trsm_upper(cudaStream_t s, char side, char trans, int m, int n, const T* U, 
   void* scr = ctx_scratch((size_t)nblk * NB * NB * sizeof(T) + 256);
   if (!scr) return -1;
   T* Dinv = (T*)scr;
-  trtri_blocks_kernel<T><<<nblk, NB, blk_smem<T>(), s>>>(U, ldu, nu, Dinv);
+  trtri_blocks_kernel<T><<<dim3(nblk, 8), 256, tri_smem<T>(), s>>>(U, ldu, nu, Dinv, 0);
   EIGB_LAUNCH_CHECK();
   return trsm_rec<T>(s, side, trans, 0, nu, other, U, ldu, B, ldb, Dinv);
 }
@@ -354,7 +373,7 @@ int hegst_upper(cudaStream_t s, int n, T* A, int64_t lda, const T* U, int64_t ld
   void* scr = ctx_scratch((size_t)nblk * NB * NB * sizeof(T) + 256);
   if (!scr) return -1;
   T* Dinv = (T*)scr;
-  trtri_blocks_kernel<T><<<nblk, NB, blk_smem<T>(), s>>>(U, ldu, n, Dinv);
+  trtri_blocks_kernel<T><<<dim3(nblk, 8), 256, tri_smem<T>(), s>>>(U, ldu, n, Dinv, 0);
   EIGB_LAUNCH_CHECK();
   const int HB = (n >= 4096) ? 2048 : 1024;
   for (int k = 0; k < n; k += HB) {
