@@ -16,9 +16,10 @@ struct Options {
   int symv_tma = 1;     // stage symv/hemv tiles through TMA (cp.async.bulk.tensor) when alignment allows
   int trd_coop = 1;     // persistent cooperative panel kernel (0: one launch per phase)
   int mg_switch_n = 3072; // multi-GPU hetrd: below this trailing order all ranks continue replicated
-  int trd_upc = 6;      // tile engine: target number of tile units per CTA (strip length heuristic)
-  int trd_prefetch = -1; // tiles per CTA prefetched into L2 during phase A (-1: auto = 256 KB, 0: off)
-  int trd_trace = 0;    // record per-column globaltimer stamps of the panel kernel (profiling aid)
+  int trd_upc = 3;      // tile engine: target number of tile units per CTA (strip length heuristic)
+  int trd_prefetch = 0; // tiles per CTA prefetched into L2 during phase A (-1: 256 KB worth, 0: off -- no gain measured)
+  int trd_trace = 0;    // 1: per-column stamps; k > 1: also a per-tile engine trace of CTA trd_trace_cta for order k
+  int trd_trace_cta = 0;    // record per-column globaltimer stamps of the panel kernel (profiling aid)
 };
 Options& opts();
 

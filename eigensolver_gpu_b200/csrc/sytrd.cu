@@ -37,6 +37,11 @@ constexpr int NTT = NT + 32;  // + one TMA producer warp
 constexpr int NWT = NTT / 32;
 constexpr int NBMAX = 128;    // max panel width
 constexpr int AW = 8;         // warps that split the per-row work in phase C (multi-GPU)
+#ifdef EIGB_ENGINE_TRACE
+constexpr bool ETRACE = true;   // per-tile engine trace (tools/trace_engine.py); costs registers in the hot loop
+#else
+constexpr bool ETRACE = false;
+#endif
 constexpr int TRSLOTS = 16;    // globaltimer stamps per column when tracing
 constexpr int MAXBANDS = 256; // max number of strip bands (tile rows / strip length), enforced by strip_len()
 
@@ -71,6 +76,7 @@ struct TrdP {
   int use_tma;                 // tiles staged through the TMA ring (needs 16-byte aligned columns)
   int upc;                     // target number of tile units per CTA (strip length heuristic)
   int npf;                     // tiles each CTA prefetches into L2 during phase A (0: off)
+  int etrace_j, etrace_cta; int64_t etrace_off;   // (debug) per-tile engine trace of one CTA for the product of order etrace_j
   unsigned long long* trace;   // optional: TRSLOTS globaltimer stamps per column (CTA 0), profiling aid
   // multi-GPU (1-D block-cyclic distribution of the 64-wide tile columns of the trailing matrix over P ranks)
   int rank, P;                 // P == 1: single GPU
@@ -127,7 +133,7 @@ struct PanelSmem {
   uint64_t full[8], empty[8];   // ring mbarriers
   TileMeta meta[8];
   ColDesc cd[2];                // descriptors of the current and the next product (parity of the panel column)
-  T hh_scale;                   // phase B: 1 / (alpha - beta) from warp 0
+  T hh_scale;                   // phase B: alpha - beta (= x~(j-1)) from warp 0
 };
 
 __device__ __forceinline__ double ldcg_(const double* p) { return __ldcg(p); }
@@ -203,9 +209,11 @@ __device__ __forceinline__ T block_sum(T v, T* red /* >= NWT entries */) {
 // tiles per strip chunk for an order-n product on G CTAs: aim at >= upc units per CTA, at most 8 tiles per unit
 __host__ __device__ __forceinline__ int strip_len(int n, int G, int P, int upc) {
   const int Tn = (n + TB - 1) / TB;
+  const int cmax = upc >> 8 ? upc >> 8 : 8;     // (tuning) bits 8.. of upc override the maximum strip length
+  upc &= 255;
   int c = (Tn * (Tn - 1) / 2) / (upc * G * P);
   if (c < 1) c = 1;
-  if (c > 8) c = 8;
+  if (c > cmax) c = cmax;
   while ((Tn - 1) / c > MAXBANDS) ++c;
   return c;
 }
@@ -395,10 +403,12 @@ template <typename T, class XR>
 __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc,
                            XR xfix, T* Pd, T* Pt, int64_t ldp, double* vavunit, unsigned* qctr, int cta, int G, bool tma,
                            T* ring, uint64_t* full, uint64_t* empty, TileMeta* meta, RingState& rs, EngineSmem<T>& es,
-                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc, int upc) {
+                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc, int upc,
+                           unsigned long long* etr = nullptr) {
   constexpr int S = RingCfg<T>::STAGES, NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int st = rs.stage;
+  int etn = 0;                                    // tile counter of the (debug) per-tile trace
 
   if (warp >= NW) {
     // ===================== producer warp =====================
@@ -406,7 +416,12 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
     for (;;) {
       const bool end = unit >= um.total;
       int J = 0, I0 = 0, I1 = 0; bool hd = false;
-      if (!end) um.decode(unit, J, I0, I1, hd);
+      int nu = 0;
+      if (!end) {
+        // take the next unit id now: the round trip of the atomic overlaps with this unit's tiles
+        if (lane == 0) nu = G + (int)atomicAdd(qctr, 1u);
+        um.decode(unit, J, I0, I1, hd);
+      }
       const int ntile = end ? 1 : (I1 - I0) + (hd ? 1 : 0);
       for (int t = 0; t < ntile; ++t) {
         const bool diag = !end && hd && (t == ntile - 1);
@@ -414,15 +429,18 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
         mbar_wait(&empty[st], (rs.par >> st) & 1u);
         rs.par ^= (1u << st);
         T* dst = ring + (size_t)st * stage_elems<T>();
+        const int m_flags_dbg = end ? MF_END : ((t == 0 ? MF_FIRST : 0) | (t == ntile - 1 ? MF_LAST : 0) | (diag ? MF_DIAG : 0));
         if (lane == 0) {
           TileMeta m;
           m.I = I; m.J = J; m.unit = unit;
-          m.flags = end ? MF_END : ((t == 0 ? MF_FIRST : 0) | (t == ntile - 1 ? MF_LAST : 0) | (diag ? MF_DIAG : 0));
+          m.flags = m_flags_dbg;
           meta[st] = m;
           if (end || !tma) mbar_arrive(&full[st]);
           else mbar_expect_tx(&full[st], (unsigned)(stage_elems<T>() * sizeof(T)));
         }
         __syncwarp();
+        if (ETRACE && etr != nullptr && lane == 0 && etn < 60) { etr[etn * 8] = clock64(); etr[etn * 8 + 7] = (unsigned long long)m_flags_dbg; }
+        ++etn;
         if (!end && tma) {
           if (lane < NBOX)
             tma_load_2d(reinterpret_cast<char*>(dst) + lane * BOX_BYTES, tmap, (I * TB) * DPE + lane * 16, J * TB, &full[st]);
@@ -432,8 +450,6 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
         st = (st + 1) % S;
       }
       if (end) break;
-      int nu = 0;
-      if (lane == 0) nu = G + (int)atomicAdd(qctr, 1u);
       unit = __shfl_sync(0xffffffffu, nu, 0);
     }
     // idle from here on: derive the next product's descriptor while the consumers drain the ring
@@ -446,6 +462,7 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
     for (;;) {
       mbar_wait(&full[st], (rs.par >> st) & 1u);
       rs.par ^= (1u << st);
+      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 1] = clock64();
       const int4 mv = *reinterpret_cast<const int4*>(&meta[st]);
       const int I = mv.x, J = mv.y, unit = mv.z, fl = mv.w;
       const int stc = st;
@@ -512,6 +529,7 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
 #pragma unroll
         for (int h = 0; h < 4; ++h) { const int gr = I * TB + r4 + h; xr[h] = xfix(gr, gr < n ? xsrc[gr] : zero_<T>()); }
       }
+      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 2] = clock64();
       // ---- products: direct (rows) and transposed (columns)
       T accd[4];
 #pragma unroll
@@ -536,12 +554,15 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
           }
         }
       }
+      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 3] = clock64() + (long long)(real_(accd[0]) == 1.234e300);
       warp_reduce4(accd, lane);
+      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 4] = clock64() + (long long)(real_(accd[0]) == 1.234e300);
       if ((lane & 7) == 0) {
         const int h = lane >> 3;
         if (!diag) Pd[(int64_t)J * ldp + I * TB + r4 + h] = accd[0];     // off-diagonal tile: all 64 rows are < n
         else es.ydiag[r4 + h] = accd[0];
       }
+      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 5] = clock64();
       if (fl & MF_LAST) {
         // strip end: combine the transposed sums of the 16 warps (+ the diagonal tile's direct part) -> Pt[band]
         es.yt[warp][lane] = acct[0];
@@ -563,6 +584,8 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
         }
         consumer_barrier();
       }
+      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 6] = clock64();
+      ++etn;
     }
   }
   rs.stage = st;
@@ -709,7 +732,7 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
           const int cc = cprev + 1 + lane + 32 * k;
           a1[k] = a2[k] = a3[k] = a4[k] = zero_<T>();
           if (cc < nbp) {
-            a1[k] = ldcg_(p.zfin + cc); a2[k] = ldcg_(p.zfin + NBMAX + cc);
+            a1[k] = mul_(scale_p, ldcg_(p.zfin + cc)); a2[k] = mul_(scale_p, ldcg_(p.zfin + NBMAX + cc));   // z = scale * (.)^H x~
             a3[k] = ldcg_(p.A + j + (int64_t)(p.i0 + cc) * p.lda); a4[k] = ldcg_(p.W + j + (int64_t)cc * p.ldw);
           }
         }
@@ -750,14 +773,15 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
         }
         zz = warp_sum(zz);
         part = warp_sum(part);
-        wj = warp_sum(wj);
+        wj = mul_(scale_p, warp_sum(wj));         // (A v)(j) = scale * (A x~)(j)
         vx = warp_sum(vx);
-        __syncthreads();                          // (#1) workers' shares of v^H A v are in dscal
+        __syncthreads();                          // (#1) workers' shares of x~^H A x~ are in dscal
         double vv = vx;
         if (!mg) {
 #pragma unroll
           for (int w = 0; w < NW; ++w) vv += sm.dscal[w];
         }
+        vv *= abs2_(scale_p);                     // v^H A v = |scale|^2 x~^H A x~
         // rho = v^H A v - 2 Re(z1^H z2), alpha' = -1/2 |tau|^2 rho, W(j, c+1) = tau (w_j - part) + alpha' (v(j) = 1)
         const double rho = vv - 2.0 * zz;
         const double alpha_p = -0.5 * abs2_(tau_p) * rho;
@@ -796,6 +820,7 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
       if (have_prev) xb = ldcg_(p.xbuf + r);
       if (c >= 0) acol = ldcg_(p.A + r + (int64_t)j * p.lda);
     }
+    const T scale_w = have_prev ? ldcg_(p.scale_slot) : zero_<T>();
     if (have_prev) {
       if (round == 0 && !mg) {
         // this thread's share of the per-unit v^H A v slots
@@ -877,7 +902,7 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
     }
     {
       T* ar = S.ared + (warp * 32 + lane) * 2;
-      ar[0] = sub_(wr, t1); ar[1] = t2;
+      ar[0] = sub_(mul_(scale_w, wr), t1); ar[1] = t2;
     }
     tstamp(p, c, 9);
     __syncthreads();                              // (#2) also: the scalar warp's results
@@ -947,7 +972,11 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
     um.bstart = nullptr;
   }
   um.rcpC = cd.rcpC;
+  // The product runs on the UNSCALED column x~ (x~(j-1) = alpha - beta, so that v = scale * x~ with
+  // scale = 1 / (alpha - beta)): no multiplication per element in the tile loop; the consumers of the partial sums
+  // (phase A) apply scale, |scale|^2 once per row / scalar.
   T scale = from_real<T>(1.0);
+  T xt = zero_<T>();
   if (warp < NW) {
     if (warp == 0) {
       double xs[5];
@@ -960,18 +989,18 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
       double beta; T tau;
       larfg_scalars(alpha, x2, beta, tau, scale);
       if (lane == 0) {
-        sm.hh_scale = scale;
+        sm.hh_scale = sub_(alpha, from_real<T>(beta));
         if (cta == 0) { p.e[j - 1] = beta; p.tau[j - 1] = tau; *p.scale_slot = scale; }
       }
     }
     consumer_barrier();
-    scale = sm.hh_scale;
+    xt = sm.hh_scale;
   }
   tstamp(p, c, 12);
-  auto xfix = [j, scale](int r, T raw) -> T {
+  auto xfix = [j, xt](int r, T raw) -> T {
     if (r >= j) return zero_<T>();
-    if (r == j - 1) return from_real<T>(1.0);
-    return mul_(scale, raw);
+    if (r == j - 1) return xt;
+    return raw;
   };
   // -- z1 = V^H v, z2 = W^H v: pair q = (which, cc) is done completely by the consumer warps of CTA G-1-q
   const int nf = p.nbp - 1 - c;      // finished columns cc in (c, nbp)
@@ -1007,7 +1036,8 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
   tstamp(p, c, 13);
   // -- the tile engine: w_raw partials and v^H A v
   engine_run<T>(um, p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, p.vavunit, p.qctr + c, cta, G, p.use_tma != 0, ring,
-                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn, p.upc);
+                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn, p.upc,
+                (p.trace != nullptr && cta == p.etrace_cta && j == p.etrace_j) ? p.trace + (size_t)p.etrace_off : nullptr);
   return um.total;
 }
 
@@ -1240,8 +1270,11 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     if (!GP) { set_last_error("hetrd: scratch arena too small (multi-GPU)"); return -1; }
   }
   if (opts().trd_trace) {
-    if (cudaMalloc(&p.trace, (size_t)n * TRSLOTS * sizeof(unsigned long long)) != cudaSuccess) p.trace = nullptr;
-    else cudaMemsetAsync(p.trace, 0, (size_t)n * TRSLOTS * sizeof(unsigned long long), s);
+    if (cudaMalloc(&p.trace, ((size_t)n * TRSLOTS + 512) * sizeof(unsigned long long)) != cudaSuccess) p.trace = nullptr;
+    else cudaMemsetAsync(p.trace, 0, ((size_t)n * TRSLOTS + 512) * sizeof(unsigned long long), s);
+    p.etrace_j = opts().trd_trace > 1 ? opts().trd_trace : -1;
+    p.etrace_cta = opts().trd_trace_cta;
+    p.etrace_off = (int64_t)n * TRSLOTS;
   }
   EIGB_CUDA_CHECK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
   const bool coop = opts().trd_coop != 0;
@@ -1332,8 +1365,8 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   EIGB_CUDA_CHECK(cudaMemcpyAsync(&st, p.status, sizeof(int), cudaMemcpyDeviceToHost, s));
   EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
   if (p.trace) {
-    trace_store().resize((size_t)n * TRSLOTS);
-    cudaMemcpy(trace_store().data(), p.trace, (size_t)n * TRSLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    trace_store().resize((size_t)n * TRSLOTS + 512);
+    cudaMemcpy(trace_store().data(), p.trace, ((size_t)n * TRSLOTS + 512) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(p.trace);
   }
   if (st != 0) { set_last_error("hetrd: device status %d (grid barrier watchdog)", st); return -1; }
