@@ -105,11 +105,14 @@ struct ColDesc {
 struct __align__(16) TileMeta { int I, J, unit, flags; };
 constexpr int MF_FIRST = 1, MF_LAST = 2, MF_DIAG = 4, MF_END = 8;
 
+// real: the strip scratch is double buffered (parity of the strip), which saves the second consumer barrier of a
+// strip end; complex keeps one buffer (shared memory is taken by the ring) and two barriers
+template <typename T> struct StripBuf { static constexpr int N = is_cplx<T>::value ? 1 : 2; };
 template <typename T>
 struct EngineSmem {
-  T yt[NW][TB];        // strip end: transposed partial sums of the 16 row-group warps (also: v slice of the z-dot units)
-  T ydiag[TB];         // D units: product of the diagonal tile with x_J (both triangles)
-  double vred[NW];     // strip end: per-warp v^H A v of the unit
+  T yt[StripBuf<T>::N][NW][TB];   // strip end: transposed partial sums of the 16 row-group warps
+  T ydiag[StripBuf<T>::N][TB];    // D units: product of the diagonal tile with x_J (both triangles)
+  double vred[StripBuf<T>::N][NW];   // strip end: per-warp v^H A v of the unit
   int bstart[MAXBANDS + 2];   // multi-GPU: prefix counts of the F units per band
 };
 template <typename T>
@@ -397,6 +400,211 @@ __device__ __forceinline__ UnitMap engine_prepare(int n, int C, int rank, int P,
   return um;
 }
 
+template <typename T>
+struct ConsumerState {
+  T acct[2];        // transposed sums of the strip (this lane's two tile columns, this warp's rows)
+  double vav;       // the unit's share of Re(x^H A x)
+  int par;          // strip parity (selects the strip scratch buffer when it is double buffered)
+};
+
+// reduction of NV per-lane values over the 32 lanes of a warp: on return lane (32/NV)*v holds the total of
+// value v in v[0] (NV = 4: 6 shuffles per scalar, NV = 8: 9)
+template <int NV>
+__device__ __forceinline__ void warp_reduce_n(double (&v)[NV], int lane) {
+  if constexpr (NV == 8) {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double s = up ? v[k] : v[k + 4];
+      const double r = __shfl_xor_sync(0xffffffffu, s, 16);
+      v[k] = (up ? v[k + 4] : v[k]) + r;
+    }
+    {
+      const bool u8 = lane & 8;
+      const double s0 = u8 ? v[0] : v[2], s1 = u8 ? v[1] : v[3];
+      const double r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
+      v[0] = (u8 ? v[2] : v[0]) + r0;
+      v[1] = (u8 ? v[3] : v[1]) + r1;
+    }
+    {
+      const bool u4 = lane & 4;
+      const double s = u4 ? v[0] : v[1];
+      const double r = __shfl_xor_sync(0xffffffffu, s, 4);
+      v[0] = (u4 ? v[1] : v[0]) + r;
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  } else {
+    double w[4] = {v[0], v[1], v[2], v[3]};
+    warp_reduce4(w, lane);
+    v[0] = w[0];
+  }
+}
+
+// One pass of a consumer warp over NP (1 or 2) tiles of the same tile column.  m[t] = {I, J, unit, flags} of
+// tile t, stg[t] its ring stage.  Warp w owns tile rows [4w, 4w+4); lane l owns tile columns l and l+32.
+template <typename T, int NP, class XR>
+__device__ __forceinline__ void process_tiles(ConsumerState<T>& cs, const int4 (&m)[NP], const int (&stg)[NP],
+                                              const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc,
+                                              XR xfix, T* Pd, T* Pt, int64_t ldp, double* vavunit, const UnitMap& um,
+                                              bool tma, T* ring, uint64_t* empty, EngineSmem<T>& es) {
+  constexpr int DPE = RingCfg<T>::DPE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r4 = 4 * warp;
+  const int J = m[0].y;
+  constexpr int NBUF = StripBuf<T>::N;
+  const int pb = NBUF > 1 ? cs.par : 0;
+  if (m[0].w & MF_FIRST) { cs.acct[0] = zero_<T>(); cs.acct[1] = zero_<T>(); cs.vav = 0.0; }
+  T a[NP][4][2], xr[NP][4], xc[2];
+  if (tma) {
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+      const T* tile = ring + (size_t)stg[t] * stage_elems<T>();
+      // this warp's 4 rows live in box (4w*DPE)/16, 16-byte chunks k0.. of each 128-byte column line; the
+      // SWIZZLE_128B layout stores chunk k of line c at chunk position k ^ (c & 7)
+      const char* box = reinterpret_cast<const char*>(tile) + ((r4 * DPE) / 16) * BOX_BYTES;
+      const int k0 = ((r4 * DPE) % 16) / 2;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = lane + 32 * q;
+        const char* line = box + c * 128;
+        if constexpr (!is_cplx<T>::value) {
+          const double2 v0 = *reinterpret_cast<const double2*>(line + (((k0) ^ (c & 7)) << 4));
+          const double2 v1 = *reinterpret_cast<const double2*>(line + (((k0 + 1) ^ (c & 7)) << 4));
+          a[t][0][q] = v0.x; a[t][1][q] = v0.y; a[t][2][q] = v1.x; a[t][3][q] = v1.y;
+        } else {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) a[t][h][q] = *reinterpret_cast<const double2*>(line + (((k0 + h) ^ (c & 7)) << 4));
+        }
+        if (t == 0) xc[q] = xfix(J * TB + c, tile[TB * TB + TB + c]);
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h) xr[t][h] = xfix(m[t].x * TB + r4 + h, tile[TB * TB + r4 + h]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < NP; ++t) mbar_arrive(&empty[stg[t]]);          // this warp is done with the stage(s)
+    }
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+      if (m[t].w & MF_DIAG) {
+        // the box also brought the (ignored) lower triangle: keep r < c, make the diagonal real
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int r = r4 + h, c = lane + 32 * q;
+            if (r > c) a[t][h][q] = zero_<T>();
+            else if (r == c) a[t][h][q] = from_real<T>(real_(a[t][h][q]));
+          }
+      }
+    }
+  } else {
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < NP; ++t) mbar_arrive(&empty[stg[t]]);          // the stage carried only the descriptor
+    }
+    // masked loads straight from global memory
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+      const int I = m[t].x;
+      const bool diag = (m[t].w & MF_DIAG) != 0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = lane + 32 * q, gc = J * TB + c;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int r = r4 + h, gr = I * TB + r;
+          const bool ok = gr < n && gc < n && (!diag || r <= c);
+          a[t][h][q] = ok ? __ldg(A + gr + (int64_t)gc * lda) : zero_<T>();
+          if (diag && r == c) a[t][h][q] = from_real<T>(real_(a[t][h][q]));    // Hermitian: real diagonal
+        }
+        if (t == 0) xc[q] = xfix(gc, gc < n ? xsrc[gc] : zero_<T>());
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h) { const int gr = I * TB + r4 + h; xr[t][h] = xfix(gr, gr < n ? xsrc[gr] : zero_<T>()); }
+    }
+  }
+  // ---- products: direct (rows) and transposed (columns)
+  T accd[NP][4];
+#pragma unroll
+  for (int t = 0; t < NP; ++t) {
+    const bool diag = (m[t].w & MF_DIAG) != 0;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      accd[t][h] = zero_<T>();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        fma_(accd[t][h], a[t][h][q], xc[q]);
+        if (!diag || (r4 + h) < (lane + 32 * q)) fmac_(cs.acct[q], a[t][h][q], xr[t][h]);
+      }
+      // v^H A v: conj(x_r) (A x)_r; an off-diagonal tile also stands for its mirror image, and so does the
+      // strictly upper part of a diagonal tile
+      if (!diag) {
+        T tt = zero_<T>(); fmac_(tt, xr[t][h], accd[t][h]);
+        cs.vav += 2.0 * real_(tt);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          T u = zero_<T>(); fma_(u, a[t][h][q], xc[q]);
+          T tt = zero_<T>(); fmac_(tt, xr[t][h], u);
+          cs.vav += ((r4 + h) < (lane + 32 * q) ? 2.0 : 1.0) * real_(tt);
+        }
+      }
+    }
+  }
+  // ---- direct sums: reduce over the lanes, store (off-diagonal tile: all 64 rows are < n)
+  if constexpr (NP == 2) {
+    double v[8];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) v[t * 4 + h] = real_(accd[t][h]);
+    warp_reduce_n<8>(v, lane);
+    if ((lane & 3) == 0) {
+      const int t = lane >> 4, h = (lane >> 2) & 3;
+      const int4 mt = t ? m[NP - 1] : m[0];
+      if (!(mt.w & MF_DIAG)) Pd[(int64_t)J * ldp + mt.x * TB + r4 + h] = from_real<T>(v[0]);
+      else es.ydiag[pb][r4 + h] = from_real<T>(v[0]);
+    }
+  } else {
+    warp_reduce4(accd[0], lane);
+    if ((lane & 7) == 0) {
+      const int h = lane >> 3;
+      if (!(m[0].w & MF_DIAG)) Pd[(int64_t)J * ldp + m[0].x * TB + r4 + h] = accd[0][0];
+      else es.ydiag[pb][r4 + h] = accd[0][0];
+    }
+  }
+  const int4 ml = m[NP - 1];
+  if (ml.w & MF_LAST) {
+    // strip end: combine the transposed sums of the 16 warps (+ the diagonal tile's direct part) -> Pt[band]
+    const bool diag = (ml.w & MF_DIAG) != 0;
+    es.yt[pb][warp][lane] = cs.acct[0];
+    es.yt[pb][warp][lane + 32] = cs.acct[1];
+    const double vs = warp_sum(cs.vav);
+    if (lane == 0) es.vred[pb][warp] = vs;
+    consumer_barrier();
+    if (tid < TB) {
+      T s = diag ? es.ydiag[pb][tid] : zero_<T>();
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s = add_(s, es.yt[pb][w][tid]);
+      const int band = ((diag ? J : ml.x) * um.rcpC) >> 16;
+      if (J * TB + tid < n) Pt[(int64_t)band * ldp + J * TB + tid] = s;
+    } else if (tid == TB) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += es.vred[pb][w];
+      vavunit[ml.z] = s;
+    }
+    // single buffer: nobody may touch the scratch before the readers are done.  Double buffer: this buffer is
+    // written again two strip ends from now, i.e. after the readers have gone through the next strip's barrier.
+    if (NBUF == 1) consumer_barrier();
+    cs.par ^= 1;
+  }
+}
+
 // XR: (global index r, raw x value) -> x(r) (must return 0 for r >= n); xsrc: x stored with at least
 // roundup64(n) readable entries.  All NTT threads must call; ends with a CTA barrier.
 template <typename T, class XR>
@@ -456,136 +664,37 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
     if (lane == 0 && next_cd != nullptr) compute_desc(*next_cd, jnext, G, Pdesc, upc);
   } else {
     // ===================== consumer warps =====================
-    const int r4 = 4 * warp;
-    T acct[2] = {zero_<T>(), zero_<T>()};
-    double vav = 0.0;
+    ConsumerState<T> cs;
+    cs.acct[0] = zero_<T>(); cs.acct[1] = zero_<T>(); cs.vav = 0.0; cs.par = 0;
     for (;;) {
       mbar_wait(&full[st], (rs.par >> st) & 1u);
       rs.par ^= (1u << st);
-      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 1] = clock64();
-      const int4 mv = *reinterpret_cast<const int4*>(&meta[st]);
-      const int I = mv.x, J = mv.y, unit = mv.z, fl = mv.w;
-      const int stc = st;
+      const int4 m0 = *reinterpret_cast<const int4*>(&meta[st]);
+      const int st0 = st;
       st = (st + 1) % S;
-      if (fl & MF_END) {
+      if (m0.w & MF_END) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stc]);
+        if (lane == 0) mbar_arrive(&empty[st0]);
         break;
       }
-      const bool diag = (fl & MF_DIAG) != 0;
-      if (fl & MF_FIRST) { acct[0] = zero_<T>(); acct[1] = zero_<T>(); vav = 0.0; }
-      T a[4][2], xr[4], xc[2];
-      if (tma) {
-        const T* tile = ring + (size_t)stc * stage_elems<T>();
-        // this warp's 4 rows live in box (4w*DPE)/16, 16-byte chunks k0.. of each 128-byte column line; the
-        // SWIZZLE_128B layout stores chunk k of line c at chunk position k ^ (c & 7)
-        const char* box = reinterpret_cast<const char*>(tile) + ((r4 * DPE) / 16) * BOX_BYTES;
-        const int k0 = ((r4 * DPE) % 16) / 2;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int c = lane + 32 * q;
-          const char* line = box + c * 128;
-          if constexpr (!is_cplx<T>::value) {
-            const double2 v0 = *reinterpret_cast<const double2*>(line + (((k0) ^ (c & 7)) << 4));
-            const double2 v1 = *reinterpret_cast<const double2*>(line + (((k0 + 1) ^ (c & 7)) << 4));
-            a[0][q] = v0.x; a[1][q] = v0.y; a[2][q] = v1.x; a[3][q] = v1.y;
-          } else {
-#pragma unroll
-            for (int h = 0; h < 4; ++h) a[h][q] = *reinterpret_cast<const double2*>(line + (((k0 + h) ^ (c & 7)) << 4));
-          }
-          xc[q] = xfix(J * TB + c, tile[TB * TB + TB + c]);
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h) xr[h] = xfix(I * TB + r4 + h, tile[TB * TB + r4 + h]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stc]);          // this warp is done with the stage
-        if (diag) {
-          // the box also brought the (ignored) lower triangle: keep r < c, make the diagonal real
-#pragma unroll
-          for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const int r = r4 + h, c = lane + 32 * q;
-              if (r > c) a[h][q] = zero_<T>();
-              else if (r == c) a[h][q] = from_real<T>(real_(a[h][q]));
-            }
-        }
-      } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stc]);          // the stage carried only the descriptor
-        // masked loads straight from global memory
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int c = lane + 32 * q, gc = J * TB + c;
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int r = r4 + h, gr = I * TB + r;
-            const bool ok = gr < n && gc < n && (!diag || r <= c);
-            a[h][q] = ok ? __ldg(A + gr + (int64_t)gc * lda) : zero_<T>();
-            if (diag && r == c) a[h][q] = from_real<T>(real_(a[h][q]));    // Hermitian: real diagonal
-          }
-          xc[q] = xfix(gc, gc < n ? xsrc[gc] : zero_<T>());
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h) { const int gr = I * TB + r4 + h; xr[h] = xfix(gr, gr < n ? xsrc[gr] : zero_<T>()); }
-      }
-      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 2] = clock64();
-      // ---- products: direct (rows) and transposed (columns)
-      T accd[4];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        accd[h] = zero_<T>();
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          fma_(accd[h], a[h][q], xc[q]);
-          if (!diag || (r4 + h) < (lane + 32 * q)) fmac_(acct[q], a[h][q], xr[h]);
-        }
-        // v^H A v: conj(x_r) (A x)_r; an off-diagonal tile also stands for its mirror image, and so does the
-        // strictly upper part of a diagonal tile
-        if (!diag) {
-          T t = zero_<T>(); fmac_(t, xr[h], accd[h]);
-          vav += 2.0 * real_(t);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            T u = zero_<T>(); fma_(u, a[h][q], xc[q]);
-            T t = zero_<T>(); fmac_(t, xr[h], u);
-            vav += ((r4 + h) < (lane + 32 * q) ? 2.0 : 1.0) * real_(t);
-          }
+      if constexpr (!is_cplx<T>::value) {
+        if (tma && !(m0.w & MF_LAST)) {
+          // real tiles are half the size of complex ones and the per-tile costs (descriptor, shuffle reduction,
+          // stores) would dominate: take the next tile of the unit (same tile column) in the same pass
+          mbar_wait(&full[st], (rs.par >> st) & 1u);
+          rs.par ^= (1u << st);
+          const int4 m1 = *reinterpret_cast<const int4*>(&meta[st]);
+          const int st1 = st;
+          st = (st + 1) % S;
+          const int4 mm[2] = {m0, m1};
+          const int ss[2] = {st0, st1};
+          process_tiles<T, 2>(cs, mm, ss, A, lda, n, xsrc, xfix, Pd, Pt, ldp, vavunit, um, tma, ring, empty, es);
+          continue;
         }
       }
-      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 3] = clock64() + (long long)(real_(accd[0]) == 1.234e300);
-      warp_reduce4(accd, lane);
-      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 4] = clock64() + (long long)(real_(accd[0]) == 1.234e300);
-      if ((lane & 7) == 0) {
-        const int h = lane >> 3;
-        if (!diag) Pd[(int64_t)J * ldp + I * TB + r4 + h] = accd[0];     // off-diagonal tile: all 64 rows are < n
-        else es.ydiag[r4 + h] = accd[0];
-      }
-      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 5] = clock64();
-      if (fl & MF_LAST) {
-        // strip end: combine the transposed sums of the 16 warps (+ the diagonal tile's direct part) -> Pt[band]
-        es.yt[warp][lane] = acct[0];
-        es.yt[warp][lane + 32] = acct[1];
-        const double vs = warp_sum(vav);
-        if (lane == 0) es.vred[warp] = vs;
-        consumer_barrier();
-        if (tid < TB) {
-          T s = diag ? es.ydiag[tid] : zero_<T>();
-#pragma unroll
-          for (int w = 0; w < NW; ++w) s = add_(s, es.yt[w][tid]);
-          const int band = ((diag ? J : I) * um.rcpC) >> 16;
-          if (J * TB + tid < n) Pt[(int64_t)band * ldp + J * TB + tid] = s;
-        } else if (tid == TB) {
-          double s = 0.0;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) s += es.vred[w];
-          vavunit[unit] = s;
-        }
-        consumer_barrier();
-      }
-      if (ETRACE && etr != nullptr && tid == 0 && etn < 60) etr[etn * 8 + 6] = clock64();
-      ++etn;
+      const int4 mm[1] = {m0};
+      const int ss[1] = {st0};
+      process_tiles<T, 1>(cs, mm, ss, A, lda, n, xsrc, xfix, Pd, Pt, ldp, vavunit, um, tma, ring, empty, es);
     }
   }
   rs.stage = st;
@@ -1005,7 +1114,7 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
   // -- z1 = V^H v, z2 = W^H v: pair q = (which, cc) is done completely by the consumer warps of CTA G-1-q
   const int nf = p.nbp - 1 - c;      // finished columns cc in (c, nbp)
   if (nf > 0 && warp < NW) {
-    T* zr = sm.u.e.ydiag;            // per-warp partial dots (the engine's scratch is not in use yet)
+    T* zr = &sm.u.e.ydiag[0][0];     // per-warp partial dots (the engine's scratch is not in use yet)
     for (int q = G - 1 - cta; q < 2 * nf; q += G) {
       const int which = q >= nf ? 1 : 0, cc = c + 1 + (q - which * nf);
       const T* col = which ? (p.W + (int64_t)cc * p.ldw) : (p.A + (int64_t)(p.i0 + cc) * p.lda);
