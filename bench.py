@@ -221,7 +221,22 @@ def main():
         if info != 0:
             raise SystemExit("solve failed: " + lib.eigb200_last_error().decode())
 
+    up_stream = torch.cuda.Stream()
+
     def step_e2e():
+        if world == 1:
+            # B first on the solver's stream; A on a second stream, overlapped with the Cholesky factorization of B
+            # (the solver waits for the event before it touches A); D2H of Z overlaps with the final solve with U
+            B.copy_(b_host, non_blocking=True)
+            up_stream.wait_stream(torch.cuda.current_stream())       # A's previous use is complete
+            ev = torch.cuda.Event()
+            with torch.cuda.stream(up_stream):
+                A.copy_(a_host, non_blocking=True)
+                ev.record(up_stream)
+            info, w, z, _ = api.solve_generalized(A, B, 1, m, ws=ws, skip_host_copy=False, a_ready_event=ev)
+            if info != 0:
+                raise SystemExit("solve failed: " + lib.eigb200_last_error().decode())
+            return
         A.copy_(a_host, non_blocking=True)
         B.copy_(b_host, non_blocking=True)
         if world > 1:

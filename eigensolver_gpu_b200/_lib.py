@@ -18,6 +18,7 @@ SIGNATURES = {
     "eigb200_finalize": (_i, []),
     "eigb200_last_error": (C.c_char_p, []),
     "eigb200_set_stream": (_i, [_p]),
+    "eigb200_set_a_ready_event": (_i, [_p]),
     "eigb200_version": (_i, []),
     "eigb200_scratch_bytes": (C.c_int64, [_i, _i]),
     "eigb200_mg_alloc": (_i, [C.c_longlong, C.POINTER(C.c_void_p), C.c_char_p]),

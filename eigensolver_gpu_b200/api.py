@@ -107,12 +107,16 @@ class Workspace:
         self.Z_h = torch.empty((n, n), dtype=dt, pin_memory=pin) if host_z else None
 
 
-def solve_generalized(a_dev, b_dev, il, iu, ws=None, skip_host_copy=True):
+def solve_generalized(a_dev, b_dev, il, iu, ws=None, skip_host_copy=True, a_ready_event=None):
     """Convenience wrapper: A,B device tensors (column-major, upper triangles used; both overwritten).
+    a_ready_event: torch.cuda.Event recorded after an asynchronous upload of A on another stream; the solver
+    factors B first and waits for the event before touching A.
     Returns (info, w_dev[all n], Z_dev view of the first m columns (as (m, n) tensor), ws)."""
     n = a_dev.shape[0]
     cplx = a_dev.dtype == torch.complex128
     ws = ws or Workspace(n, cplx, device=a_dev.device, host_z=not skip_host_copy)
+    if a_ready_event is not None:
+        load().eigb200_set_a_ready_event(C.c_void_p(a_ready_event.cuda_event))
     if cplx:
         info = zhegvdx_gpu(n, a_dev, n, b_dev, n, ws.Z, n, il, iu, ws.w, ws.work, ws.lwork, ws.rwork, ws.lrwork, None,
                            ws.lwork_h, None, ws.lrwork_h, None, ws.liwork_h, ws.Z_h, n, ws.w_h, skip_host_copy)

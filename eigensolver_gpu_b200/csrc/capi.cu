@@ -23,6 +23,7 @@ int eigb200_finalize(void) {
 }
 const char* eigb200_last_error(void) { return last_error(); }
 int eigb200_set_stream(void* s) { ctx().stream = (cudaStream_t)s; return 0; }
+int eigb200_set_a_ready_event(void* ev) { ctx().a_ready = (cudaEvent_t)ev; return 0; }
 int eigb200_version(void) { return 100; }
 
 // ---- multi-GPU plumbing for the distributed tridiagonalization -------------------------------------------------

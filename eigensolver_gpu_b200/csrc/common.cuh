@@ -89,6 +89,7 @@ struct Context {
                                  // like the reference's cuBLAS-legacy/default-stream ordering)
   cudaStream_t stream2 = nullptr;  // side stream for overlap (created lazily)
   cudaEvent_t ev1 = nullptr, ev2 = nullptr;
+  cudaEvent_t a_ready = nullptr;   // one-shot: the generalized driver waits for it before touching A
   void* scratch = nullptr;       // growable device scratch (stedc, panel partials, ...)
   size_t scratch_bytes = 0;
   int* d_info = nullptr;         // device-side status words

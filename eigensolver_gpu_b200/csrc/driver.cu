@@ -106,6 +106,12 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
     *info = -1;
     return -1;
   }
+  // a caller that uploads A asynchronously on another stream while B is being factored hands over the event of
+  // that copy (eigb200_set_a_ready_event, one-shot): wait for it before A is touched
+  if (ctx().a_ready != nullptr) {
+    EIGB_CUDA_CHECK(cudaStreamWaitEvent(s, ctx().a_ready, 0));
+    ctx().a_ready = nullptr;
+  }
   // tril(A) -> Z, A <- U^-H A U^-1 (zhegvdx_gpu.F90:145-158)
   prof_begin(PROF_HEGST, s);
   int hrc = hegst_upper<T>(s, n, A, lda, B, ldb, Z, ldz);
@@ -120,9 +126,43 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
     *info = -1;
     return -1;
   }
-  // eigenvectors of the generalized problem: Z <- U^-1 Z (zhegvdx_gpu.F90:169)
+  // eigenvectors of the generalized problem: Z <- U^-1 Z (zhegvdx_gpu.F90:169).  With a host copy requested the
+  // solve runs by column blocks and the D2H of a finished block overlaps with the solve of the next one on a side
+  // stream (the reference does one blocking cudaMemcpy2D after the trsm, zhegvdx_gpu.F90:172-180).
+  const bool want_z = skip_host_copy == 0 && Z_h != nullptr;
+  Context& c = ctx();
   prof_begin(PROF_TRSM, s);
-  int trc = trsm_upper<T>(s, 'L', 'N', n, m, B, ldb, Z, ldz);
+  int trc = 0;
+  if (want_z && c.stream2 != nullptr && c.ev1 != nullptr && m >= 1024) {
+    const int nblk = m >= 4096 ? 4 : 2;
+    const int cb = (((m + nblk - 1) / nblk) + 63) & ~63;
+    cudaEvent_t evs[4] = {nullptr, nullptr, nullptr, nullptr};
+    int ne = 0;
+    for (int c0 = 0; c0 < m && trc == 0; c0 += cb, ++ne) {
+      const int mc = m - c0 < cb ? m - c0 : cb;
+      trc = trsm_upper<T>(s, 'L', 'N', n, mc, B, ldb, Z + (int64_t)c0 * ldz, ldz);
+      if (trc != 0) break;
+      if (cudaEventCreateWithFlags(&evs[ne], cudaEventDisableTiming) != cudaSuccess) { trc = -1; break; }
+      cudaEventRecord(evs[ne], s);
+      cudaStreamWaitEvent(c.stream2, evs[ne], 0);
+      if (cudaMemcpy2DAsync(Z_h + (int64_t)c0 * ldz_h, (size_t)ldz_h * sizeof(T), Z + (int64_t)c0 * ldz,
+                            (size_t)ldz * sizeof(T), (size_t)n * sizeof(T), mc, cudaMemcpyDeviceToHost, c.stream2)
+          != cudaSuccess) trc = -1;
+    }
+    prof_end(PROF_TRSM, s);
+    if (trc == 0 && w_h) {
+      if (cudaMemcpyAsync(w_h, w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) trc = -1;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c.stream2), e2 = cudaStreamSynchronize(s);
+    for (int i = 0; i < 4; ++i) if (evs[i]) cudaEventDestroy(evs[i]);
+    if (trc != 0 || e1 != cudaSuccess || e2 != cudaSuccess) {
+      printf(" %s error: solve with U / copy to host failed!\n", name);
+      *info = -1;
+      return -1;
+    }
+    return 0;
+  }
+  trc = trsm_upper<T>(s, 'L', 'N', n, m, B, ldb, Z, ldz);
   prof_end(PROF_TRSM, s);
   if (trc != 0) { *info = -1; return -1; }
   if (copy_results_to_host<T>(s, n, m, Z, ldz, w, Z_h, ldz_h, w_h, skip_host_copy != 0) != 0) {

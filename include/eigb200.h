@@ -25,6 +25,10 @@ int eigb200_init(void);                         /* idempotent; init_eigsolve_gpu
 int eigb200_finalize(void);
 const char* eigb200_last_error(void);
 int eigb200_set_stream(void* cuda_stream);      /* stream the hot path is issued on (default: legacy stream 0) */
+/* one-shot: the next eigb200_{d,z}*gvdx call waits for this cudaEvent_t before it touches A (B is factored first), so
+ * that a caller can upload A on a second stream while the Cholesky factorization of B runs; no reference analogue
+ * (the reference's callers own the H2D copies, test_driver/test_zhegvdx.F90:266-293) */
+int eigb200_set_a_ready_event(void* cuda_event);
 int eigb200_version(void);
 /* device scratch (bytes) the library allocates internally for order n (it never asks the caller for more
  * device workspace than the reference minima) */

@@ -135,3 +135,27 @@ def test_standard_entry_points(cplx):
     assert np.abs(w - wr).max() < n * metrics.EPS * np.linalg.norm(a, 2)
     g = metrics.std_gates(a, w[il - 1:iu], z)
     assert g["residual_max"] < 30 and g["orth"] < 30
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_overlapped_upload_of_a(cplx):
+    """eigb200_set_a_ready_event: A uploaded on a second stream while B is being factored; same result as the plain call"""
+    from eigensolver_gpu_b200 import api, stages as S
+    n, m = 1200, 1200
+    a, b = matgen.family_c(n, cplx, seed=77)
+    info0, w0, z0, *_ = _solve(a, b, 1, m)
+    assert info0 == 0
+    dt = torch.complex128 if cplx else torch.float64
+    a_host = torch.from_numpy(np.ascontiguousarray(np.triu(a).T)).pin_memory()       # column-major image
+    bd = S.to_dev(np.triu(b))
+    ad = torch.empty((n, n), dtype=dt, device="cuda")
+    side = torch.cuda.Stream()
+    ev = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        ad.copy_(a_host, non_blocking=True)
+        ev.record(side)
+    info, w, z, ws = api.solve_generalized(ad, bd, 1, m, skip_host_copy=False, a_ready_event=ev)
+    assert info == 0
+    assert np.array_equal(S.to_host(w), w0)
+    assert np.array_equal(np.array(S.to_host(z)), z0)
+    assert np.array_equal(ws.Z_h.numpy().T[:, :m], z0)
