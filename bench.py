@@ -314,9 +314,20 @@ def main():
     panel_launches = max(pcnt[2] // args.steps, 1)
     hb = hemv_bytes_model(n, cplx)
     achieved = hb / (panel_ms_per_solve * 1e-3) * 1e-9 if panel_ms_per_solve > 0 else 0.0
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (one launch of the same workload)
+    traffic, traffic_note = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f).get(f"{'zhegvdx' if cplx else 'dsygvdx'}_n{n}")
+        if tr:
+            traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+            traffic_note = (f"ncu capture of ONE launch ({tr['capture']}): algorithmic bytes of that launch "
+                            f"{tr['algorithmic_bytes_of_that_launch']:.3g}; the average launch moves algorithmic_bytes_per_launch")
+    except Exception:
+        pass
     roofline = {"kernel": "panel_coop_kernel (hetrd panel: symv/hemv tiles + Householder column phases)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": hb / panel_launches, "launches_per_step": panel_launches,
                 "avg_launch_ms": panel_ms_per_solve / panel_launches}
     line = {
