@@ -131,6 +131,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "symv_tma")) { o.symv_tma = value; return 0; }
   if (!strcmp(name, "trd_coop")) { o.trd_coop = value; return 0; }
   if (!strcmp(name, "trd_trace")) { o.trd_trace = value; return 0; }
+  if (!strcmp(name, "trsm_leaf256")) { o.trsm_leaf256 = value; return 0; }
   if (!strcmp(name, "trd_trace_cta")) { o.trd_trace_cta = value; return 0; }
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
   if (!strcmp(name, "trd_prefetch")) { if (value < -1 || value > 64) return -1; o.trd_prefetch = value; return 0; }
@@ -144,6 +145,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "bt_nb")) return o.bt_nb;
   if (!strcmp(name, "symv_tma")) return o.symv_tma;
   if (!strcmp(name, "trd_coop")) return o.trd_coop;
+  if (!strcmp(name, "trsm_leaf256")) return o.trsm_leaf256;
   if (!strcmp(name, "trd_upc")) return o.trd_upc;
   if (!strcmp(name, "trd_prefetch")) return o.trd_prefetch;
   if (!strcmp(name, "mg_switch_n")) return o.mg_switch_n;

@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "stages.cuh"
+#include <vector>
+#include <string.h>
 
 namespace eigb200 {
 
@@ -239,22 +241,56 @@ int restore_lower(cudaStream_t s, int n, T* A, int64_t lda, const T* save, int64
 }
 
 // ---- recursive building blocks --------------------------------------------------------------------------
-// Splitting [lo, hi) at a multiple of 64 near the middle turns almost all flops into GEMMs with a large inner
-// dimension (half of them at K = n/2, a quarter at K = n/4, ...), which is where the DMMA kernel is efficient;
-// only the 64-wide leaves use the inverted diagonal blocks.
-static inline int split_point(int lo, int hi) {
+// Splitting [lo, hi) near the middle turns almost all flops into GEMMs with a large inner dimension (half of
+// them at K = n/2, a quarter at K = n/4, ...), which is where the DMMA kernel is efficient; only the leaves use
+// inverted diagonal blocks: 64 x 64 ones (diag_mult_kernel) while a factorization is still in progress, 256 x 256
+// ones applied by the GEMM kernel (out of place + copy back) once U is final -- a quarter of the leaves, and the
+// launches below 256 (the latency-bound part of a solve) disappear.
+constexpr int LB = 256;    // large leaf
+template <typename T>
+struct TriInv {
+  const T* d64 = nullptr;      // [ceil(n/64)][64*64]
+  const T* d256 = nullptr;     // [ceil(n/256)][256*256] or nullptr
+  T* tmp = nullptr;            // out-of-place result of a 256-leaf
+  size_t tmp_elems = 0;
+};
+template <typename T>
+static inline int split_point(int lo, int hi, const TriInv<T>& ti) {
+  if (ti.d256 && (lo % LB) == 0 && hi - lo > LB) {
+    const int nb = (hi - lo + LB - 1) / LB;
+    return lo + (nb / 2) * LB;
+  }
   const int nb = (hi - lo + NB - 1) / NB;
   return lo + (nb / 2) * NB;
 }
 
 // Triangular solve restricted to the diagonal range [lo, hi) of U.  B is addressed with GLOBAL indices:
 //   side 'L': rows [lo, hi) of B, `other` columns;   side 'R': columns [lo, hi) of B, `other` rows.
-// Dinv[b] must hold the inverse of the b-th 64x64 diagonal block of U for every block in the range.
 template <typename T>
 int trsm_rec(cudaStream_t s, char side, char trans, int lo, int hi, int other, const T* U, int64_t ldu, T* B,
-             int64_t ldb, const T* Dinv) {
+             int64_t ldb, const TriInv<T>& ti) {
+  if (ti.d256 && (lo % LB) == 0 && hi - lo <= LB && hi - lo > NB && ti.tmp_elems >= (size_t)LB * 64) {
+    const T* M = ti.d256 + (int64_t)(lo / LB) * LB * LB;
+    const int nb = hi - lo;
+    const int chunk = (int)((ti.tmp_elems / LB) < (size_t)other ? (ti.tmp_elems / LB) : (size_t)other);
+    for (int o0 = 0; o0 < other; o0 += chunk) {
+      const int oc = other - o0 < chunk ? other - o0 : chunk;
+      if (side == 'L') {
+        T* Bp = B + lo + (int64_t)o0 * ldb;                  // nb x oc
+        if (gemm<T>(s, trans == 'N' ? 'N' : 'C', 'N', nb, oc, nb, 1.0, M, LB, Bp, ldb, 0.0, ti.tmp, LB) != 0) return -1;
+        EIGB_CUDA_CHECK(cudaMemcpy2DAsync(Bp, (size_t)ldb * sizeof(T), ti.tmp, (size_t)LB * sizeof(T), (size_t)nb * sizeof(T),
+                                          oc, cudaMemcpyDeviceToDevice, s));
+      } else {
+        T* Bp = B + o0 + (int64_t)lo * ldb;                  // oc x nb
+        if (gemm<T>(s, 'N', 'N', oc, nb, nb, 1.0, Bp, ldb, M, LB, 0.0, ti.tmp, oc) != 0) return -1;
+        EIGB_CUDA_CHECK(cudaMemcpy2DAsync(Bp, (size_t)ldb * sizeof(T), ti.tmp, (size_t)oc * sizeof(T), (size_t)oc * sizeof(T),
+                                          nb, cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    return 0;
+  }
   if (hi - lo <= NB) {
-    const T* M = Dinv + (int64_t)(lo / NB) * NB * NB;
+    const T* M = ti.d64 + (int64_t)(lo / NB) * NB * NB;
     const int nb = hi - lo;
     if (other >= 120 * NB) {
       if (side == 'L' && trans == 'N')
@@ -274,27 +310,129 @@ int trsm_rec(cudaStream_t s, char side, char trans, int lo, int hi, int other, c
     EIGB_LAUNCH_CHECK();
     return 0;
   }
-  const int mid = split_point(lo, hi);
+  const int mid = split_point<T>(lo, hi, ti);
   const int n1 = mid - lo, n2 = hi - mid;
   const T* U12 = U + lo + (int64_t)mid * ldu;          // n1 x n2
   if (side == 'L' && trans == 'N') {                   // X2 = U22^-1 B2 ; B1 -= U12 X2 ; X1 = U11^-1 B1
-    if (trsm_rec<T>(s, side, trans, mid, hi, other, U, ldu, B, ldb, Dinv) != 0) return -1;
+    if (trsm_rec<T>(s, side, trans, mid, hi, other, U, ldu, B, ldb, ti) != 0) return -1;
     if (gemm<T>(s, 'N', 'N', n1, other, n2, -1.0, U12, ldu, B + mid, ldb, 1.0, B + lo, ldb) != 0) return -1;
-    return trsm_rec<T>(s, side, trans, lo, mid, other, U, ldu, B, ldb, Dinv);
+    return trsm_rec<T>(s, side, trans, lo, mid, other, U, ldu, B, ldb, ti);
   } else if (side == 'L') {                            // X1 = U11^-H B1 ; B2 -= U12^H X1 ; X2 = U22^-H B2
-    if (trsm_rec<T>(s, side, trans, lo, mid, other, U, ldu, B, ldb, Dinv) != 0) return -1;
+    if (trsm_rec<T>(s, side, trans, lo, mid, other, U, ldu, B, ldb, ti) != 0) return -1;
     if (gemm<T>(s, 'C', 'N', n2, other, n1, -1.0, U12, ldu, B + lo, ldb, 1.0, B + mid, ldb) != 0) return -1;
-    return trsm_rec<T>(s, side, trans, mid, hi, other, U, ldu, B, ldb, Dinv);
+    return trsm_rec<T>(s, side, trans, mid, hi, other, U, ldu, B, ldb, ti);
   } else {                                             // X1 = B1 U11^-1 ; B2 -= X1 U12 ; X2 = B2 U22^-1
-    if (trsm_rec<T>(s, side, trans, lo, mid, other, U, ldu, B, ldb, Dinv) != 0) return -1;
+    if (trsm_rec<T>(s, side, trans, lo, mid, other, U, ldu, B, ldb, ti) != 0) return -1;
     if (gemm<T>(s, 'N', 'N', other, n2, n1, -1.0, B + (int64_t)lo * ldb, ldb, U12, ldu, 1.0, B + (int64_t)mid * ldb, ldb)
         != 0) return -1;
-    return trsm_rec<T>(s, side, trans, mid, hi, other, U, ldu, B, ldb, Dinv);
+    return trsm_rec<T>(s, side, trans, mid, hi, other, U, ldu, B, ldb, ti);
   }
+}
+
+// 64x64 inverse blocks -> the block diagonal of the 256x256 inverse blocks (everything else zero)
+template <typename T>
+__global__ void dinv_place_kernel(const T* __restrict__ d64, int nblk64, T* d256) {
+  const int b = blockIdx.x;                         // 64-block
+  if (b >= nblk64) return;
+  T* dst = d256 + (int64_t)(b / 4) * LB * LB + (int64_t)(b % 4) * NB * (LB + 1);
+  const T* src = d64 + (int64_t)b * NB * NB;
+  for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) dst[(idx & (NB - 1)) + (int64_t)(idx >> 6) * LB] = src[idx];
+}
+
+// Scratch (in elements of T unless noted) of a solve with a finished factor of order nu and `other` right-hand sides
+template <typename T>
+size_t triinv_scratch_bytes(int nu, int other) {
+  const size_t nb64 = (size_t)cdiv(nu, NB), nb256 = (size_t)cdiv(nu, LB);
+  size_t tmp = (size_t)LB * (size_t)(other < 64 ? 64 : other);
+  const size_t cap = (size_t)LB * 16384;             // 256 x 16384 elements at most, larger panels go in chunks
+  if (tmp > cap) tmp = cap;
+  return (nb64 * NB * NB + nb256 * LB * LB + nb256 * 2 * 128 * 128 + tmp) * sizeof(T) + (4 * nb256 + 8) * sizeof(GemmParams<T>) + 4096;
+}
+
+// Inverses of the diagonal blocks of the finished factor U: 64x64 by substitution (trtri_blocks_kernel), then two
+// batched merge levels  inv([A B; 0 C]) = [A^-1, -A^-1 B C^-1; 0, C^-1]  (4 device-parameter GEMM launches for the
+// whole matrix) up to 256x256.  Carves everything from the context scratch.
+template <typename T>
+int build_triinv(cudaStream_t s, int nu, int other, const T* U, int64_t ldu, TriInv<T>& ti) {
+  const int nb64 = cdiv(nu, NB), nb256 = cdiv(nu, LB);
+  const bool big = opts().trsm_leaf256 != 0 && nu > LB;
+  void* scr = ctx_scratch(big ? triinv_scratch_bytes<T>(nu, other) : (size_t)nb64 * NB * NB * sizeof(T) + 256);
+  if (!scr) return -1;
+  Arena ar(scr, ctx().scratch_bytes);
+  T* d64 = ar.take<T>((size_t)nb64 * NB * NB);
+  trtri_blocks_kernel<T><<<dim3(nb64, 8), 256, tri_smem<T>(), s>>>(U, ldu, nu, d64, 0);
+  EIGB_LAUNCH_CHECK();
+  ti.d64 = d64;
+  if (!big) return 0;
+  T* d256 = ar.take<T>((size_t)nb256 * LB * LB);
+  T* t1 = ar.take<T>((size_t)nb256 * 2 * 128 * 128);
+  size_t tmp = (size_t)LB * (size_t)(other < 64 ? 64 : other);
+  if (tmp > (size_t)LB * 16384) tmp = (size_t)LB * 16384;
+  T* tmpb = ar.take<T>(tmp);
+  GemmParams<T>* GP = ar.take<GemmParams<T>>((size_t)4 * nb256 + 8);
+  if (!GP) { set_last_error("trsm: scratch arena too small"); return -1; }
+  EIGB_CUDA_CHECK(cudaMemsetAsync(d256, 0, (size_t)nb256 * LB * LB * sizeof(T), s));
+  dinv_place_kernel<T><<<nb64, 256, 0, s>>>(d64, nb64, d256);
+  EIGB_LAUNCH_CHECK();
+  // parameter blocks: [0, n1) level-1 first products, [n1, 2 n1) level-1 second products, then level 2 likewise
+  std::vector<GemmParams<T>> hp;
+  auto mk = [&](int M, int N, int K, const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, double alpha) {
+    GemmParams<T> g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.N = N; g.nseg = 1;
+    g.A[0] = A; g.lda[0] = lda; g.B[0] = B; g.ldb[0] = ldb; g.K[0] = K;
+    g.A[1] = A; g.lda[1] = lda; g.B[1] = B; g.ldb[1] = ldb; g.K[1] = 0;
+    g.sa[0] = g.sa[1] = 1.0; g.sb[0] = g.sb[1] = 1.0;
+    g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = 0.0; g.mode = 0; g.real_diag = 0; g.colmap = nullptr;
+    hp.push_back(g);
+  };
+  // level 1: 64-block pairs (2p, 2p+1) inside a 256 block
+  int cnt1 = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int p2 = 0; 2 * p2 + 1 < nb64; ++p2) {
+      const int b0 = 2 * p2, b1 = b0 + 1;
+      const int w = (nu - b1 * NB) < NB ? nu - b1 * NB : NB;          // width of the second block
+      T* blk = d256 + (int64_t)(b0 / 4) * LB * LB;
+      const int o0 = (b0 % 4) * NB, o1 = o0 + NB;                      // offsets inside the 256 block
+      T* t = t1 + (int64_t)p2 * NB * NB;
+      if (pass == 0) mk(NB, w, NB, blk + o0 + (int64_t)o0 * LB, LB, U + b0 * NB + (int64_t)b1 * NB * ldu, ldu, t, NB, 1.0);
+      else           mk(NB, w, w, t, NB, blk + o1 + (int64_t)o1 * LB, LB, blk + o0 + (int64_t)o1 * LB, LB, -1.0);
+      if (pass == 0) ++cnt1;
+    }
+  }
+  // level 2: halves of a 256 block
+  int cnt2 = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int q = 0; q < nb256; ++q) {
+      const int r0 = q * LB, c0 = r0 + 128;
+      if (c0 >= nu) continue;
+      const int w = (nu - c0) < 128 ? nu - c0 : 128;
+      T* blk = d256 + (int64_t)q * LB * LB;
+      T* t = t1 + (int64_t)q * 128 * 128;
+      if (pass == 0) mk(128, w, 128, blk, LB, U + r0 + (int64_t)c0 * ldu, ldu, t, 128, 1.0);
+      else           mk(128, w, w, t, 128, blk + 128 + (int64_t)128 * LB, LB, blk + (int64_t)128 * LB, LB, -1.0);
+      if (pass == 0) ++cnt2;
+    }
+  }
+  if (!hp.empty()) {
+    EIGB_CUDA_CHECK(cudaMemcpyAsync(GP, hp.data(), sizeof(GemmParams<T>) * hp.size(), cudaMemcpyHostToDevice, s));
+    GemmParams<T> dummy{};
+    if (cnt1 > 0) {
+      if (gemm_launch<T>(s, false, true, dummy, GP, cnt1, NB, NB) != 0) return -1;
+      if (gemm_launch<T>(s, false, true, dummy, GP + cnt1, cnt1, NB, NB) != 0) return -1;
+    }
+    if (cnt2 > 0) {
+      if (gemm_launch<T>(s, false, true, dummy, GP + 2 * cnt1, cnt2, 128, 128) != 0) return -1;
+      if (gemm_launch<T>(s, false, true, dummy, GP + 2 * cnt1 + cnt2, cnt2, 128, 128) != 0) return -1;
+    }
+  }
+  ti.d256 = d256; ti.tmp = tmpb; ti.tmp_elems = tmp;
+  return 0;
 }
 
 template <typename T>
 int potrf_rec(cudaStream_t s, int lo, int hi, T* A, int64_t lda, T* Dinv, int* dinfo) {
+  TriInv<T> ti; ti.d64 = Dinv;
   if (hi - lo <= NB) {
     potf2_block_kernel<T><<<1, 256, tri_smem<T>(), s>>>(A, lda, lo, hi - lo, dinfo);
     EIGB_LAUNCH_CHECK();
@@ -302,11 +440,11 @@ int potrf_rec(cudaStream_t s, int lo, int hi, T* A, int64_t lda, T* Dinv, int* d
     EIGB_LAUNCH_CHECK();
     return 0;
   }
-  const int mid = split_point(lo, hi);
+  const int mid = split_point<T>(lo, hi, ti);
   if (potrf_rec<T>(s, lo, mid, A, lda, Dinv, dinfo) != 0) return -1;
   // U12 = U11^-H A12 : rows [lo, mid) of the column block [mid, hi)
   T* A12cols = A + (int64_t)mid * lda;
-  if (trsm_rec<T>(s, 'L', 'C', lo, mid, hi - mid, A, lda, A12cols, lda, Dinv) != 0) return -1;
+  if (trsm_rec<T>(s, 'L', 'C', lo, mid, hi - mid, A, lda, A12cols, lda, ti) != 0) return -1;
   // A22 -= U12^H U12 (upper)
   if (herk_upper<T>(s, 'C', hi - mid, mid - lo, -1.0, A + lo + (int64_t)mid * lda, lda, 1.0,
                     A + mid + (int64_t)mid * lda, lda) != 0) return -1;
@@ -342,13 +480,9 @@ int trsm_upper(cudaStream_t s, char side, char trans, int m, int n, const T* U, 
   if (enable_all_smem<T>() != 0) return -1;
   const int nu = (side == 'L') ? m : n;
   const int other = (side == 'L') ? n : m;
-  const int nblk = cdiv(nu, NB);
-  void* scr = ctx_scratch((size_t)nblk * NB * NB * sizeof(T) + 256);
-  if (!scr) return -1;
-  T* Dinv = (T*)scr;
-  trtri_blocks_kernel<T><<<dim3(nblk, 8), 256, tri_smem<T>(), s>>>(U, ldu, nu, Dinv, 0);
-  EIGB_LAUNCH_CHECK();
-  return trsm_rec<T>(s, side, trans, 0, nu, other, U, ldu, B, ldb, Dinv);
+  TriInv<T> ti;
+  if (build_triinv<T>(s, nu, other, U, ldu, ti) != 0) return -1;
+  return trsm_rec<T>(s, side, trans, 0, nu, other, U, ldu, B, ldb, ti);
 }
 
 // Reduction to standard form A <- U^-H A U^-1 (zhegst_gpu.F90:31-109 / dsygst_gpu.F90:31-98).
@@ -369,12 +503,8 @@ int hegst_upper(cudaStream_t s, int n, T* A, int64_t lda, const T* U, int64_t ld
     // which is harmless: only the upper triangle is read afterwards
     if (symmetrize_from_upper<T>(s, n, A, lda, save, lds) != 0) return -1;
   }
-  const int nblk = cdiv(n, NB);
-  void* scr = ctx_scratch((size_t)nblk * NB * NB * sizeof(T) + 256);
-  if (!scr) return -1;
-  T* Dinv = (T*)scr;
-  trtri_blocks_kernel<T><<<dim3(nblk, 8), 256, tri_smem<T>(), s>>>(U, ldu, n, Dinv, 0);
-  EIGB_LAUNCH_CHECK();
+  TriInv<T> Dinv;
+  if (build_triinv<T>(s, n, n, U, ldu, Dinv) != 0) return -1;
   const int HB = (n >= 4096) ? 2048 : 1024;
   for (int k = 0; k < n; k += HB) {
     const int kb = n - k < HB ? n - k : HB;
