@@ -131,6 +131,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "symv_tma")) { o.symv_tma = value; return 0; }
   if (!strcmp(name, "trd_coop")) { o.trd_coop = value; return 0; }
   if (!strcmp(name, "trd_trace")) { o.trd_trace = value; return 0; }
+  if (!strcmp(name, "trd_l2keep_mb")) { if (value < 0 || value > 4096) return -1; o.trd_l2keep_mb = value; return 0; }
   if (!strcmp(name, "trsm_leaf256")) { o.trsm_leaf256 = value; return 0; }
   if (!strcmp(name, "trd_trace_cta")) { o.trd_trace_cta = value; return 0; }
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
@@ -145,6 +146,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "bt_nb")) return o.bt_nb;
   if (!strcmp(name, "symv_tma")) return o.symv_tma;
   if (!strcmp(name, "trd_coop")) return o.trd_coop;
+  if (!strcmp(name, "trd_l2keep_mb")) return o.trd_l2keep_mb;
   if (!strcmp(name, "trsm_leaf256")) return o.trsm_leaf256;
   if (!strcmp(name, "trd_upc")) return o.trd_upc;
   if (!strcmp(name, "trd_prefetch")) return o.trd_prefetch;

@@ -75,6 +75,7 @@ struct TrdP {
   int* status;
   int use_tma;                 // tiles staged through the TMA ring (needs 16-byte aligned columns)
   int upc;                     // target number of tile units per CTA (strip length heuristic)
+  int keepI;                   // L2 residency: tile rows < keepI are loaded with evict_last (0: no cache hints)
   int npf;                     // tiles each CTA prefetches into L2 during phase A (0: off)
   int etrace_j, etrace_cta; int64_t etrace_off;   // (debug) per-tile engine trace of one CTA for the product of order etrace_j
   unsigned long long* trace;   // optional: TRSLOTS globaltimer stamps per column (CTA 0), profiling aid
@@ -170,6 +171,13 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
                :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// same with an L2 eviction-priority policy (createpolicy)
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;\n"
+               :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n"
@@ -286,6 +294,7 @@ __device__ __forceinline__ void larfg_scalars(double2 alpha, double xnorm2, doub
 // =====================================================================================================
 struct UnitMap {
   int Tn, C, rcpC, rank, P, TnO, KB, NF, total;
+  int keepI;            // tiles of tile rows < keepI are loaded with L2 evict_last, the others with evict_first (0: no hints)
   const int* bstart;    // P > 1: bstart[k] = number of F units in bands < k (shared memory, KB+1 entries)
   // owned tile columns are J = rank + P*jj, jj = 0..TnO-1
   __device__ __forceinline__ int first_owned_at_least(int Jmin) const {   // smallest jj with rank + P*jj >= Jmin
@@ -301,7 +310,7 @@ struct UnitMap {
   // number of bands that have F units at all: (k+1)*C < Tn
   __device__ __forceinline__ static int num_bands(int Tn_, int C_) { return Tn_ > 0 ? (Tn_ - 1) / C_ : 0; }
   __device__ __forceinline__ void init(int n, int C_, int rank_, int P_, const int* bstart_) {
-    Tn = (n + TB - 1) / TB; C = C_; rcpC = (65536 + C_ - 1) / C_; rank = rank_; P = P_; bstart = bstart_;
+    Tn = (n + TB - 1) / TB; C = C_; rcpC = (65536 + C_ - 1) / C_; rank = rank_; P = P_; bstart = bstart_; keepI = 0;
     TnO = rank < Tn ? (Tn - rank + P - 1) / P : 0;
     KB = num_bands(Tn, C);
     NF = (P == 1) ? prefix1(KB) : (KB > 0 ? bstart[KB] : 0);
@@ -620,6 +629,14 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
 
   if (warp >= NW) {
     // ===================== producer warp =====================
+    // L2 residency: the tile stream of one column (up to 0.5 GB) would evict everything else -- the partial sums,
+    // V and W that phase A reads back -- and itself before the next column comes round.  Tiles of the top tile rows
+    // (a fixed subset that fits in L2) are kept with evict_last, the rest streams through with evict_first.
+    uint64_t pol_keep = 0, pol_stream = 0;
+    if (um.keepI > 0) {
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol_keep));
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol_stream));
+    }
     int unit = cta;                       // first unit static, the following ones from the queue
     for (;;) {
       const bool end = unit >= um.total;
@@ -650,8 +667,13 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
         if (ETRACE && etr != nullptr && lane == 0 && etn < 60) { etr[etn * 8] = clock64(); etr[etn * 8 + 7] = (unsigned long long)m_flags_dbg; }
         ++etn;
         if (!end && tma) {
-          if (lane < NBOX)
-            tma_load_2d(reinterpret_cast<char*>(dst) + lane * BOX_BYTES, tmap, (I * TB) * DPE + lane * 16, J * TB, &full[st]);
+          if (lane < NBOX) {
+            if (um.keepI > 0)
+              tma_load_2d_hint(reinterpret_cast<char*>(dst) + lane * BOX_BYTES, tmap, (I * TB) * DPE + lane * 16, J * TB, &full[st],
+                               I < um.keepI ? pol_keep : pol_stream);
+            else
+              tma_load_2d(reinterpret_cast<char*>(dst) + lane * BOX_BYTES, tmap, (I * TB) * DPE + lane * 16, J * TB, &full[st]);
+          }
           else if (lane == NBOX) bulk_copy_g2s(dst + TB * TB, xsrc + I * TB, (unsigned)(TB * sizeof(T)), &full[st]);
           else if (lane == NBOX + 1) bulk_copy_g2s(dst + TB * TB + TB, xsrc + J * TB, (unsigned)(TB * sizeof(T)), &full[st]);
         }
@@ -1081,6 +1103,8 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
     um.bstart = nullptr;
   }
   um.rcpC = cd.rcpC;
+  // cache hints only while the triangle of this product exceeds what L2 can hold anyway
+  um.keepI = ((int64_t)cd.Tn * cd.Tn * (int64_t)(TB * TB * sizeof(T) / 2) > ((int64_t)96 << 20)) ? p.keepI : 0;
   // The product runs on the UNSCALED column x~ (x~(j-1) = alpha - beta, so that v = scale * x~ with
   // scale = 1 / (alpha - beta)): no multiplication per element in the tile loop; the consumers of the partial sums
   // (phase A) apply scale, |scale|^2 once per row / scalar.
@@ -1360,6 +1384,16 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   p.qctr = p.barrier + 64;
   p.use_tma = use_tma;
   p.upc = opts().trd_upc;
+  {
+    // tiles of the top keepI tile rows: keepI * Tn * tile_bytes ~ trd_l2keep_mb; only when the triangle exceeds L2
+    const double tile_mb = (double)(TB * TB * sizeof(T)) / (1 << 20);
+    const double tri_mb = 0.5 * Tnn * Tnn * tile_mb;
+    p.keepI = 0;
+    if (use_tma && opts().trd_l2keep_mb > 0 && tri_mb > 100.0) {
+      p.keepI = (int)(opts().trd_l2keep_mb / (tile_mb * (double)Tnn));
+      if (p.keepI < 1) p.keepI = 1;
+    }
+  }
   p.npf = use_tma ? (opts().trd_prefetch >= 0 ? opts().trd_prefetch : (is_cplx<T>::value ? 4 : 8)) : 0;
   p.trace = nullptr;
   MgConfig& M = mg();
