@@ -93,6 +93,7 @@ struct TrdP {
 struct RingState {
   int stage;
   unsigned par;
+  unsigned strips;   // consumers: strip ends seen so far (phase of the single-buffered strip scratch barrier)
 };
 
 // per-column descriptor, see compute_desc()
@@ -357,12 +358,14 @@ struct UnitMap {
 __device__ __forceinline__ void ring_init(uint64_t* full, uint64_t* empty, int stages, RingState& rs) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    mbar_init(&full[7], 3);       // "strip scratch free": the three reducing warps of a strip end arrive
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();
   rs.stage = 0;
   rs.par = (threadIdx.x >= NT) ? 0xffffffffu : 0u;
+  rs.strips = 0;
 }
 
 // sum of 4 per-lane values over the 32 lanes of a warp with 6 shuffles per scalar: on return lane 8*h holds the
@@ -456,14 +459,20 @@ template <typename T, int NP, class XR>
 __device__ __forceinline__ void process_tiles(ConsumerState<T>& cs, const int4 (&m)[NP], const int (&stg)[NP],
                                               const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc,
                                               XR xfix, T* Pd, T* Pt, int64_t ldp, double* vavunit, const UnitMap& um,
-                                              bool tma, T* ring, uint64_t* empty, EngineSmem<T>& es) {
+                                              bool tma, T* ring, uint64_t* empty, EngineSmem<T>& es, uint64_t* ytfree,
+                                              RingState& rs) {
   constexpr int DPE = RingCfg<T>::DPE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r4 = 4 * warp;
   const int J = m[0].y;
   constexpr int NBUF = StripBuf<T>::N;
   const int pb = NBUF > 1 ? cs.par : 0;
-  if (m[0].w & MF_FIRST) { cs.acct[0] = zero_<T>(); cs.acct[1] = zero_<T>(); cs.vav = 0.0; }
+  if (m[0].w & MF_FIRST) {
+    cs.acct[0] = zero_<T>(); cs.acct[1] = zero_<T>(); cs.vav = 0.0;
+    // single-buffered strip scratch (ydiag, yt, vred): the readers of the previous strip end must be done; they
+    // arrived long ago in practice, so this costs one already-complete try_wait instead of a second CTA-wide barrier
+    if (NBUF == 1) mbar_wait(ytfree, (rs.strips & 1u) ^ 1u);
+  }
   T a[NP][4][2], xr[NP][4], xc[2];
   if (tma) {
 #pragma unroll
@@ -607,9 +616,14 @@ __device__ __forceinline__ void process_tiles(ConsumerState<T>& cs, const int4 (
       for (int w = 0; w < NW; ++w) s += es.vred[pb][w];
       vavunit[ml.z] = s;
     }
-    // single buffer: nobody may touch the scratch before the readers are done.  Double buffer: this buffer is
-    // written again two strip ends from now, i.e. after the readers have gone through the next strip's barrier.
-    if (NBUF == 1) consumer_barrier();
+    // single buffer: the readers signal the "scratch free" barrier, checked at the start of the next unit.  Double
+    // buffer: this buffer is written again two strip ends from now, i.e. after the readers have gone through the
+    // next strip's barrier.
+    if (NBUF == 1 && tid < TB + 32) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(ytfree);
+    }
+    rs.strips += 1;
     cs.par ^= 1;
   }
 }
@@ -710,13 +724,13 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
           st = (st + 1) % S;
           const int4 mm[2] = {m0, m1};
           const int ss[2] = {st0, st1};
-          process_tiles<T, 2>(cs, mm, ss, A, lda, n, xsrc, xfix, Pd, Pt, ldp, vavunit, um, tma, ring, empty, es);
+          process_tiles<T, 2>(cs, mm, ss, A, lda, n, xsrc, xfix, Pd, Pt, ldp, vavunit, um, tma, ring, empty, es, &full[7], rs);
           continue;
         }
       }
       const int4 mm[1] = {m0};
       const int ss[1] = {st0};
-      process_tiles<T, 1>(cs, mm, ss, A, lda, n, xsrc, xfix, Pd, Pt, ldp, vavunit, um, tma, ring, empty, es);
+      process_tiles<T, 1>(cs, mm, ss, A, lda, n, xsrc, xfix, Pd, Pt, ldp, vavunit, um, tma, ring, empty, es, &full[7], rs);
     }
   }
   rs.stage = st;
