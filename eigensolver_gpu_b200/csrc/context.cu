@@ -133,7 +133,6 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "trd_trace")) { o.trd_trace = value; return 0; }
   if (!strcmp(name, "trd_l2keep_mb")) { if (value < 0 || value > 4096) return -1; o.trd_l2keep_mb = value; return 0; }
   if (!strcmp(name, "trsm_leaf256")) { o.trsm_leaf256 = value; return 0; }
-  if (!strcmp(name, "trd_trace_cta")) { o.trd_trace_cta = value; return 0; }
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
   if (!strcmp(name, "trd_prefetch")) { if (value < -1 || value > 64) return -1; o.trd_prefetch = value; return 0; }
   if (!strcmp(name, "mg_switch_n")) { o.mg_switch_n = value; return 0; }

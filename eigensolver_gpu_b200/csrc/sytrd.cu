@@ -37,11 +37,6 @@ constexpr int NTT = NT + 32;  // + one TMA producer warp
 constexpr int NWT = NTT / 32;
 constexpr int NBMAX = 128;    // max panel width
 constexpr int AW = 8;         // warps that split the per-row work in phase C (multi-GPU)
-#ifdef EIGB_ENGINE_TRACE
-constexpr bool ETRACE = true;   // per-tile engine trace (tools/trace_engine.py); costs registers in the hot loop
-#else
-constexpr bool ETRACE = false;
-#endif
 constexpr int TRSLOTS = 16;    // globaltimer stamps per column when tracing
 constexpr int MAXBANDS = 256; // max number of strip bands (tile rows / strip length), enforced by strip_len()
 
@@ -77,7 +72,7 @@ struct TrdP {
   int upc;                     // target number of tile units per CTA (strip length heuristic)
   int keepI;                   // L2 residency: tile rows < keepI are loaded with evict_last (0: no cache hints)
   int npf;                     // tiles each CTA prefetches into L2 during phase A (0: off)
-  int etrace_j, etrace_cta; int64_t etrace_off;   // (debug) per-tile engine trace of one CTA for the product of order etrace_j
+  int etrace_j; int64_t etrace_off;   // (profiling aid) per-CTA begin/end stamps of phase B for the product of order etrace_j
   unsigned long long* trace;   // optional: TRSLOTS globaltimer stamps per column (CTA 0), profiling aid
   // multi-GPU (1-D block-cyclic distribution of the 64-wide tile columns of the trailing matrix over P ranks)
   int rank, P;                 // P == 1: single GPU
@@ -634,12 +629,10 @@ template <typename T, class XR>
 __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc,
                            XR xfix, T* Pd, T* Pt, int64_t ldp, double* vavunit, unsigned* qctr, int cta, int G, bool tma,
                            T* ring, uint64_t* full, uint64_t* empty, TileMeta* meta, RingState& rs, EngineSmem<T>& es,
-                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc, int upc,
-                           unsigned long long* etr = nullptr) {
+                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc, int upc) {
   constexpr int S = RingCfg<T>::STAGES, NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int st = rs.stage;
-  int etn = 0;                                    // tile counter of the (debug) per-tile trace
 
   if (warp >= NW) {
     // ===================== producer warp =====================
@@ -668,18 +661,15 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
         mbar_wait(&empty[st], (rs.par >> st) & 1u);
         rs.par ^= (1u << st);
         T* dst = ring + (size_t)st * stage_elems<T>();
-        const int m_flags_dbg = end ? MF_END : ((t == 0 ? MF_FIRST : 0) | (t == ntile - 1 ? MF_LAST : 0) | (diag ? MF_DIAG : 0));
         if (lane == 0) {
           TileMeta m;
           m.I = I; m.J = J; m.unit = unit;
-          m.flags = m_flags_dbg;
+          m.flags = end ? MF_END : ((t == 0 ? MF_FIRST : 0) | (t == ntile - 1 ? MF_LAST : 0) | (diag ? MF_DIAG : 0));
           meta[st] = m;
           if (end || !tma) mbar_arrive(&full[st]);
           else mbar_expect_tx(&full[st], (unsigned)(stage_elems<T>() * sizeof(T)));
         }
         __syncwarp();
-        if (ETRACE && etr != nullptr && lane == 0 && etn < 60) { etr[etn * 8] = clock64(); etr[etn * 8 + 7] = (unsigned long long)m_flags_dbg; }
-        ++etn;
         if (!end && tma) {
           if (lane < NBOX) {
             if (um.keepI > 0)
@@ -1183,8 +1173,7 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
   tstamp(p, c, 13);
   // -- the tile engine: w_raw partials and v^H A v
   engine_run<T>(um, p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, p.vavunit, p.qctr + c, cta, G, p.use_tma != 0, ring,
-                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn, p.upc,
-                (p.trace != nullptr && cta == p.etrace_cta && j == p.etrace_j) ? p.trace + (size_t)p.etrace_off : nullptr);
+                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn, p.upc);
   return um.total;
 }
 
@@ -1256,7 +1245,10 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
     target += gridDim.x;
     grid_barrier(p.barrier, target, p.status, false, [&]() { store_npart(p, sm); });
     stamp(c, 2);
+    const bool spread = p.trace != nullptr && p.i0 + c == p.etrace_j && threadIdx.x == 0;   // per-CTA begin/end of phase B
+    if (spread) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.trace[p.etrace_off + 512 + blockIdx.x] = t; }
     const int total_units = phase_b<T, MG>(p, c, sm, ring, rs, &tmap, sm.cd[c & 1], &sm.cd[(c + 1) & 1]);
+    if (spread) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.trace[p.etrace_off + 768 + blockIdx.x] = t; }
     stamp(c, 3);
     target += gridDim.x;
     grid_barrier(p.barrier, target, p.status, false, []() {});
@@ -1427,10 +1419,9 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     if (!GP) { set_last_error("hetrd: scratch arena too small (multi-GPU)"); return -1; }
   }
   if (opts().trd_trace) {
-    if (cudaMalloc(&p.trace, ((size_t)n * TRSLOTS + 512) * sizeof(unsigned long long)) != cudaSuccess) p.trace = nullptr;
-    else cudaMemsetAsync(p.trace, 0, ((size_t)n * TRSLOTS + 512) * sizeof(unsigned long long), s);
+    if (cudaMalloc(&p.trace, ((size_t)n * TRSLOTS + 1024) * sizeof(unsigned long long)) != cudaSuccess) p.trace = nullptr;
+    else cudaMemsetAsync(p.trace, 0, ((size_t)n * TRSLOTS + 1024) * sizeof(unsigned long long), s);
     p.etrace_j = opts().trd_trace > 1 ? opts().trd_trace : -1;
-    p.etrace_cta = opts().trd_trace_cta;
     p.etrace_off = (int64_t)n * TRSLOTS;
   }
   EIGB_CUDA_CHECK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
@@ -1522,8 +1513,8 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   EIGB_CUDA_CHECK(cudaMemcpyAsync(&st, p.status, sizeof(int), cudaMemcpyDeviceToHost, s));
   EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
   if (p.trace) {
-    trace_store().resize((size_t)n * TRSLOTS + 512);
-    cudaMemcpy(trace_store().data(), p.trace, ((size_t)n * TRSLOTS + 512) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    trace_store().resize((size_t)n * TRSLOTS + 1024);
+    cudaMemcpy(trace_store().data(), p.trace, ((size_t)n * TRSLOTS + 1024) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(p.trace);
   }
   if (st != 0) { set_last_error("hetrd: device status %d (grid barrier watchdog)", st); return -1; }
