@@ -553,12 +553,9 @@ __device__ __forceinline__ void process_tiles(ConsumerState<T>& cs, const int4 (
         fma_(accd[t][h], a[t][h][q], xc[q]);
         if (!diag || (r4 + h) < (lane + 32 * q)) fmac_(cs.acct[q], a[t][h][q], xr[t][h]);
       }
-      // v^H A v: conj(x_r) (A x)_r; an off-diagonal tile also stands for its mirror image, and so does the
-      // strictly upper part of a diagonal tile
-      if (!diag) {
-        T tt = zero_<T>(); fmac_(tt, xr[t][h], accd[t][h]);
-        cs.vav += 2.0 * real_(tt);
-      } else {
+      // v^H A v: conj(x_r) (A x)_r; an off-diagonal tile also stands for its mirror image (done after the lane
+      // reduction below, on the row totals), and so does the strictly upper part of a diagonal tile
+      if (diag) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           T u = zero_<T>(); fma_(u, a[t][h][q], xc[q]);
@@ -579,15 +576,32 @@ __device__ __forceinline__ void process_tiles(ConsumerState<T>& cs, const int4 (
     if ((lane & 3) == 0) {
       const int t = lane >> 4, h = (lane >> 2) & 3;
       const int4 mt = t ? m[NP - 1] : m[0];
-      if (!(mt.w & MF_DIAG)) Pd[(int64_t)J * ldp + mt.x * TB + r4 + h] = from_real<T>(v[0]);
-      else es.ydiag[pb][r4 + h] = from_real<T>(v[0]);
+      if (!(mt.w & MF_DIAG)) {
+        Pd[(int64_t)J * ldp + mt.x * TB + r4 + h] = from_real<T>(v[0]);
+        T xh = xr[0][0];
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) if (tt == t && hh == h) xh = xr[tt][hh];
+        cs.vav += 2.0 * real_(xh) * v[0];
+      } else {
+        es.ydiag[pb][r4 + h] = from_real<T>(v[0]);
+      }
     }
   } else {
     warp_reduce4(accd[0], lane);
     if ((lane & 7) == 0) {
       const int h = lane >> 3;
-      if (!(m[0].w & MF_DIAG)) Pd[(int64_t)J * ldp + m[0].x * TB + r4 + h] = accd[0][0];
-      else es.ydiag[pb][r4 + h] = accd[0][0];
+      if (!(m[0].w & MF_DIAG)) {
+        Pd[(int64_t)J * ldp + m[0].x * TB + r4 + h] = accd[0][0];
+        T xh = xr[0][0];
+#pragma unroll
+        for (int hh = 1; hh < 4; ++hh) if (hh == h) xh = xr[0][hh];
+        T tt = zero_<T>(); fmac_(tt, xh, accd[0][0]);
+        cs.vav += 2.0 * real_(tt);
+      } else {
+        es.ydiag[pb][r4 + h] = accd[0][0];
+      }
     }
   }
   const int4 ml = m[NP - 1];

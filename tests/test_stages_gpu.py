@@ -89,3 +89,30 @@ def test_ormtr(cplx, n, m, nb):
     got = S.to_host(zd)
     ref = lapack.ormtr("L", "U", "N", a2, tau, z) if n > 1 else z
     assert np.abs(got - ref).max() <= 50 * n * metrics.EPS * np.abs(z).max()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_trsm_leaf_sizes_agree(cplx):
+    """solves with a finished factor: 256x256 inverted leaves (default) and 64x64 leaves give the same solution"""
+    import numpy as np
+    from eigensolver_gpu_b200 import stages as S
+    from eigensolver_gpu_b200._lib import load
+    from oracle import matgen, metrics
+    lib = load()
+    n, m = 900, 333                               # partial last 256-block, partial last 64-block
+    _, b = matgen.family_c(n, cplx, seed=4)
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((n, m)) + (1j * rng.standard_normal((n, m)) if cplx else 0)
+    bd = S.to_dev(np.triu(b))
+    assert S.potrf(bd) == 0
+    u = np.triu(np.array(S.to_host(bd)))
+    sols = []
+    for leaf in (1, 0):
+        assert lib.eigb200_set_option(b"trsm_leaf256", leaf) == 0
+        xd = S.to_dev(x)
+        S.trsm("L", "N", bd, xd, m=n, n=m)
+        sols.append(np.array(S.to_host(xd)))
+    lib.eigb200_set_option(b"trsm_leaf256", 1)
+    for sol in sols:
+        r = u @ sol - x
+        assert np.abs(r).max() <= 50 * n * metrics.EPS * np.abs(u).max() * np.abs(sol).max()

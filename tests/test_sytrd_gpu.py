@@ -61,3 +61,39 @@ def test_hetrd_matches_lapack(cplx, n, nb, coop):
         z = lapack.ormtr("L", "U", "N", np.asfortranarray(aout), tau, zt.astype(aout.dtype))
         g = metrics.std_gates(a, w, z)
         assert g["residual_max"] < 30 and g["orth"] < 30
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("opt,val", [("trd_l2keep_mb", 0), ("trd_l2keep_mb", 1), ("trd_upc", 6), ("trd_upc", 1 + (2 << 8)),
+                                     ("trd_prefetch", 4)])
+def test_hetrd_tuning_options_do_not_change_the_result_class(cplx, opt, val):
+    """scheduling / cache-policy knobs of the tile engine: same (d, e) as LAPACK to rounding whatever their value"""
+    from eigensolver_gpu_b200 import stages as S
+    from eigensolver_gpu_b200._lib import load
+    lib = load()
+    n = 1700
+    old = lib.eigb200_get_option(opt.encode())
+    assert lib.eigb200_set_option(opt.encode(), val) == 0
+    try:
+        a = _herm(n, cplx, 11)
+        ad = S.to_dev(np.triu(a))
+        d, e, tau = S.hetrd(ad)
+        d, e = S.to_host(d), S.to_host(e)
+    finally:
+        lib.eigb200_set_option(opt.encode(), old)
+    _, dl, el, _ = lapack.hetrd(a)
+    tol = 20 * n * metrics.EPS * np.abs(a).sum(axis=0).max()
+    assert np.abs(d - dl).max() <= tol and np.abs(e - el).max() <= tol
+
+
+def test_hetrd_is_run_to_run_deterministic():
+    """the dynamic tile queue decides WHO runs a unit, never WHAT is summed in which order: bitwise identical repeats"""
+    from eigensolver_gpu_b200 import stages as S
+    a = _herm(2300, True, 5)
+    outs = []
+    for _ in range(3):
+        ad = S.to_dev(np.triu(a))
+        d, e, tau = S.hetrd(ad)
+        outs.append((S.to_host(d).copy(), S.to_host(e).copy(), S.to_host(tau).copy()))
+    for o in outs[1:]:
+        assert all(np.array_equal(x, y) for x, y in zip(outs[0], o))
