@@ -73,6 +73,7 @@ void* ctx_scratch(size_t bytes) {
 }  // namespace eigb200
 
 #include "stages.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include <vector>
 namespace eigb200 {
 
@@ -91,12 +92,17 @@ static cudaEvent_t prof_event() {
   if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
+// NVTX3 ranges around the stages (header-only: the injection library is loaded by the tools, nothing is linked) --
+// the counterpart of the reference's nvtx_inters module (toolbox.F90:25-99), including its optional device sync
+static const char* kStageNames[PROF_NCAT] = {"potrf", "hegst", "hetrd_panel", "hetrd_her2k", "stedc", "ormtr", "trsm", "other"};
 void prof_begin(int cat, cudaStream_t s) {
+  if (opts().nvtx) { if (opts().nvtx > 1) cudaStreamSynchronize(s); nvtxRangePushA(kStageNames[cat]); }
   if (!g_prof_on) return;
   g_open[cat] = prof_event();
   cudaEventRecord(g_open[cat], s);
 }
 void prof_end(int cat, cudaStream_t s) {
+  if (opts().nvtx) { if (opts().nvtx > 1) cudaStreamSynchronize(s); nvtxRangePop(); }
   if (!g_prof_on) return;
   cudaEvent_t b = prof_event();
   cudaEventRecord(b, s);
@@ -131,6 +137,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "symv_tma")) { o.symv_tma = value; return 0; }
   if (!strcmp(name, "trd_coop")) { o.trd_coop = value; return 0; }
   if (!strcmp(name, "trd_trace")) { o.trd_trace = value; return 0; }
+  if (!strcmp(name, "nvtx")) { o.nvtx = value; return 0; }
   if (!strcmp(name, "trd_l2keep_mb")) { if (value < 0 || value > 4096) return -1; o.trd_l2keep_mb = value; return 0; }
   if (!strcmp(name, "trsm_leaf256")) { o.trsm_leaf256 = value; return 0; }
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
@@ -145,6 +152,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "bt_nb")) return o.bt_nb;
   if (!strcmp(name, "symv_tma")) return o.symv_tma;
   if (!strcmp(name, "trd_coop")) return o.trd_coop;
+  if (!strcmp(name, "nvtx")) return o.nvtx;
   if (!strcmp(name, "trd_l2keep_mb")) return o.trd_l2keep_mb;
   if (!strcmp(name, "trsm_leaf256")) return o.trsm_leaf256;
   if (!strcmp(name, "trd_upc")) return o.trd_upc;

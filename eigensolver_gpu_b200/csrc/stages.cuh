@@ -20,6 +20,7 @@ struct Options {
   int trd_prefetch = 0; // tiles per CTA prefetched into L2 during phase A (-1: 256 KB worth, 0: off -- no gain measured)
   int trsm_leaf256 = 1; // solves with a finished factor: 256x256 inverted diagonal blocks applied by the GEMM kernel
   int trd_l2keep_mb = 32; // tile engine: MB of the trailing matrix (its top tile rows) kept in L2 with evict_last; 0: no hints
+  int nvtx = 0;         // 1: NVTX3 range per stage; 2: with a stream synchronisation at both ends (toolbox.F90:71-97)
   int trd_trace = 0;    // 1: per-column stamps; k > 1: also per-CTA begin/end stamps of phase B for the product of order k    // record per-column globaltimer stamps of the panel kernel (profiling aid)
 };
 Options& opts();
