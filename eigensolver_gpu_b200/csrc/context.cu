@@ -138,6 +138,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "trd_coop")) { o.trd_coop = value; return 0; }
   if (!strcmp(name, "trd_trace")) { o.trd_trace = value; return 0; }
   if (!strcmp(name, "nvtx")) { o.nvtx = value; return 0; }
+  if (!strcmp(name, "hegst_hb")) { if (value < 0) return -1; o.hegst_hb = value; return 0; }
   if (!strcmp(name, "trd_l2keep_mb")) { if (value < 0 || value > 4096) return -1; o.trd_l2keep_mb = value; return 0; }
   if (!strcmp(name, "trsm_leaf256")) { o.trsm_leaf256 = value; return 0; }
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
@@ -153,6 +154,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "symv_tma")) return o.symv_tma;
   if (!strcmp(name, "trd_coop")) return o.trd_coop;
   if (!strcmp(name, "nvtx")) return o.nvtx;
+  if (!strcmp(name, "hegst_hb")) return o.hegst_hb;
   if (!strcmp(name, "trd_l2keep_mb")) return o.trd_l2keep_mb;
   if (!strcmp(name, "trsm_leaf256")) return o.trsm_leaf256;
   if (!strcmp(name, "trd_upc")) return o.trd_upc;

@@ -134,9 +134,9 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
   prof_begin(PROF_TRSM, s);
   int trc = 0;
   if (want_z && c.stream2 != nullptr && c.ev1 != nullptr && m >= 1024) {
-    const int nblk = m >= 4096 ? 4 : 2;
+    const int nblk = m >= 8192 ? 8 : (m >= 4096 ? 4 : 2);
     const int cb = (((m + nblk - 1) / nblk) + 63) & ~63;
-    cudaEvent_t evs[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int ne = 0;
     for (int c0 = 0; c0 < m && trc == 0; c0 += cb, ++ne) {
       const int mc = m - c0 < cb ? m - c0 : cb;
@@ -154,7 +154,7 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
       if (cudaMemcpyAsync(w_h, w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) trc = -1;
     }
     cudaError_t e1 = cudaStreamSynchronize(c.stream2), e2 = cudaStreamSynchronize(s);
-    for (int i = 0; i < 4; ++i) if (evs[i]) cudaEventDestroy(evs[i]);
+    for (int i = 0; i < 8; ++i) if (evs[i]) cudaEventDestroy(evs[i]);
     if (trc != 0 || e1 != cudaSuccess || e2 != cudaSuccess) {
       printf(" %s error: solve with U / copy to host failed!\n", name);
       *info = -1;

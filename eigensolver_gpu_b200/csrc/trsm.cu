@@ -505,7 +505,7 @@ int hegst_upper(cudaStream_t s, int n, T* A, int64_t lda, const T* U, int64_t ld
   }
   TriInv<T> Dinv;
   if (build_triinv<T>(s, n, n, U, ldu, Dinv) != 0) return -1;
-  const int HB = (n >= 4096) ? 2048 : 1024;
+  const int HB = opts().hegst_hb > 0 ? ((opts().hegst_hb + LB - 1) / LB) * LB : ((n >= 4096) ? 2048 : 1024);
   for (int k = 0; k < n; k += HB) {
     const int kb = n - k < HB ? n - k : HB;
     const int r = n - k - kb;
