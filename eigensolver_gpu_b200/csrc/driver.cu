@@ -134,7 +134,7 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
   prof_begin(PROF_TRSM, s);
   int trc = 0;
   if (want_z && c.stream2 != nullptr && c.ev1 != nullptr && m >= 1024) {
-    const int nblk = m >= 8192 ? 8 : (m >= 4096 ? 4 : 2);
+    const int nblk = m >= 4096 ? 4 : 2;
     const int cb = (((m + nblk - 1) / nblk) + 63) & ~63;
     cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int ne = 0;
