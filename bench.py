@@ -112,7 +112,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": metric_name(args), "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "c128" if cplx else "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "c128" if cplx else "f64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -333,7 +333,7 @@ def main():
     line = {
         "metric": metric_name(args), "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak",
+        "scaling": "strong",            # one fixed problem whatever the number of GPUs
         "vs_baseline": None, "dtype": "c128" if cplx else "f64", "data": "synthetic",
         "config": workload_config(args),
         "clocks": clocks,
