@@ -255,15 +255,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    ncu_range = [os.environ.get("EIGB_NCU_RANGE") == "1"]     # ncu --profile-from-start off: capture the timed steps only
+
     def timed(fn, steps):
         barrier()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
+        if ncu_range[0]:
+            torch.cuda.profiler.start()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
+        if ncu_range[0]:
+            torch.cuda.profiler.stop()
+            ncu_range[0] = False                                   # the device-resident steps only, not the e2e ones
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
