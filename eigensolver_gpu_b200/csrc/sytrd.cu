@@ -5,18 +5,25 @@
 // dsymv_gpu.F90:33-150) and the final-block kernel zhetd2_gpu/dsytd2_gpu.
 //
 // Design (B200-first, not the reference's 4 launches per column with FP64 atomics):
-//  * one persistent cooperative kernel per panel (1 CTA of 512 threads per SM), 2 grid barriers per column:
-//      phase A (row-parallel "vector" phase): finish W(:,c+1) from the previous column's partial sums,
-//              bring column c up to date with the panel's reflectors, partial norms;
-//      phase B (tile phase): every CTA derives the Householder scalars (larfg) redundantly, then streams its
-//              share of the 64x64 tiles of the upper triangle ONCE through a shared-memory ring filled by
-//              cp.async.bulk (TMA, SASS UBLKCP) and uses each tile for A_IJ x_J and A_IJ^H x_I; tiles are
-//              walked in column strips so that the transposed sums stay in registers for a whole strip and
-//              only one CTA barrier per tile is needed.  The V^H v / W^H v partial dots and v^H A v ride along.
-//  * all cross-CTA reductions go through partial buffers summed in a fixed order: deterministic, no FP64
-//    atomics (the reference's results depend on atomicAdd ordering).
+//  * one persistent cooperative kernel per panel (1 CTA of 16 worker warps + 1 TMA producer warp per SM), 2 grid
+//    barriers per column:
+//      phase A (row-parallel): finish W(:,c+1) from the previous column's partial sums, store the reflector,
+//              bring column c up to date with the panel's reflectors, partial norms.  The worker warps own a block
+//              of rows; the producer warp (idle here) gathers and derives everything common to all rows.
+//      phase B (tile phase): warp 0 derives the Householder scalars while the producer warp already streams 64x64
+//              tiles of the upper triangle ONCE through a shared-memory ring filled by cp.async.bulk.tensor (TMA,
+//              SASS UTMALDG, SWIZZLE_128B, L2 eviction hints); each tile serves A_IJ x_J and A_IJ^H x_I.  Tiles are
+//              walked in column strips (transposed sums stay in registers for a strip, no CTA barrier per tile) and
+//              handed out through an atomic queue in longest-processing-time order.  The z-dot units (V^H x, W^H x)
+//              are complete per-CTA dot products that ride in front of the queue.
+//  * the product runs on the unscaled column (no multiplication by the Householder scale per element); everything
+//    that needs integer divisions is derived one column ahead by an otherwise idle thread (ColDesc).
+//  * all cross-CTA reductions go through slots determined by the work unit and summed in a fixed order:
+//    deterministic whatever CTA ran a unit, no FP64 atomics (the reference's results depend on atomicAdd ordering).
 //  * w^H v is obtained algebraically (v^H A v - 2 Re(z1^H z2)), which removes a third barrier per column.
 //  * the same panel code runs down to column 1, so no separate unblocked 32x32 kernel is needed.
+//  * MG variant: tile columns distributed 1-D block-cyclically over P GPUs, partial w exchanged through
+//    peer-mapped buffers with flag signalling inside the kernel (phase C).
 #include "common.cuh"
 #include "gemm.cuh"
 #include "stages.cuh"
