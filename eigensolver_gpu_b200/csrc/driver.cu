@@ -68,6 +68,9 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
   const bool cplx = is_cplx<T>::value;
   *info = 0;
   const char* name = cplx ? "zhegvdx_gpu" : "dsygvdx_gpu";
+  // the "A is ready" event is one-shot: consumed by this call whatever its outcome
+  cudaEvent_t a_ready = ctx().a_ready;
+  ctx().a_ready = nullptr;
   const int64_t N = n;
   // workspace checks: zhegvdx_gpu.F90:106-127 / dsygvdx_gpu.F90:100-113 (64-bit arithmetic: the reference's
   // 1+5N+2N*N overflows default integers at N >= 32767)
@@ -108,10 +111,7 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
   }
   // a caller that uploads A asynchronously on another stream while B is being factored hands over the event of
   // that copy (eigb200_set_a_ready_event, one-shot): wait for it before A is touched
-  if (ctx().a_ready != nullptr) {
-    EIGB_CUDA_CHECK(cudaStreamWaitEvent(s, ctx().a_ready, 0));
-    ctx().a_ready = nullptr;
-  }
+  if (a_ready != nullptr) EIGB_CUDA_CHECK(cudaStreamWaitEvent(s, a_ready, 0));
   // tril(A) -> Z, A <- U^-H A U^-1 (zhegvdx_gpu.F90:145-158)
   prof_begin(PROF_HEGST, s);
   int hrc = hegst_upper<T>(s, n, A, lda, B, ldb, Z, ldz);
