@@ -28,6 +28,7 @@
 #include "gemm.cuh"
 #include "stages.cuh"
 #include "tmap.cuh"
+#include "unitmap.cuh"
 #include <vector>
 #include <string.h>
 
@@ -37,7 +38,7 @@ std::vector<unsigned long long>& trace_store() { static std::vector<unsigned lon
 
 namespace {
 
-constexpr int TB = 64;        // symv/hemv tile edge
+using tile::TB; using tile::MAXBANDS; using tile::ColDesc; using tile::UnitMap; using tile::strip_len; using tile::compute_desc;
 constexpr int NT = 512;       // consumer/worker threads per CTA (16 warps: 4 tile rows each)
 constexpr int NW = NT / 32;
 constexpr int NTT = NT + 32;  // + one TMA producer warp
@@ -45,7 +46,6 @@ constexpr int NWT = NTT / 32;
 constexpr int NBMAX = 128;    // max panel width
 constexpr int AW = 8;         // warps that split the per-row work in phase C (multi-GPU)
 constexpr int TRSLOTS = 16;    // globaltimer stamps per column when tracing
-constexpr int MAXBANDS = 256; // max number of strip bands (tile rows / strip length), enforced by strip_len()
 
 // Ring of tile stages filled by TMA.  One stage = a 64x64 tile + the x slices of the tile's rows and columns.
 // A tile arrives as NBOX boxes of 16 doubles x 64 columns (8 KB each, one cp.async.bulk.tensor.2d per box) in the
@@ -96,13 +96,6 @@ struct RingState {
   int stage;
   unsigned par;
   unsigned strips;   // consumers: strip ends seen so far (phase of the single-buffered strip scratch barrier)
-};
-
-// per-column descriptor, see compute_desc()
-struct ColDesc {
-  int j, Tn, C, rcpC, KB, NF, total;   // order, tile rows, strip length (+ 2^16 reciprocal), unit map (P == 1)
-  int R;                               // rows per CTA in the phase A that follows
-  int ndj, nsj;                        // partial-sum slots of the last row (direct / total)
 };
 
 // what the producer warp tells the consumers about the tile in a ring stage
@@ -220,38 +213,6 @@ __device__ __forceinline__ T block_sum(T v, T* red /* >= NWT entries */) {
   return s;
 }
 
-// tiles per strip chunk for an order-n product on G CTAs: aim at >= upc units per CTA, at most 8 tiles per unit
-__host__ __device__ __forceinline__ int strip_len(int n, int G, int P, int upc) {
-  const int Tn = (n + TB - 1) / TB;
-  const int cmax = upc >> 8 ? upc >> 8 : 8;     // (tuning) bits 8.. of upc override the maximum strip length
-  upc &= 255;
-  int c = (Tn * (Tn - 1) / 2) / (upc * G * P);
-  if (c < 1) c = 1;
-  if (c > cmax) c = cmax;
-  while ((Tn - 1) / c > MAXBANDS) ++c;
-  return c;
-}
-
-// Everything a CTA needs to know about the product of order j (panel column c).  It is used by phase B(c) and by
-// the phase A that follows (c-1) and is derived one column ahead by a single thread that would otherwise idle
-// (the producer warp, after its last tile): integer divisions and square roots cost ~25 dependent instructions
-// each, and 17 warps repeating them on the critical path of every column was a measurable part of it.
-__device__ void compute_desc(ColDesc& d, int j, int G, int P, int upc) {
-  d.j = j;
-  if (j <= 0) { d.Tn = 0; d.C = 1; d.rcpC = 65536; d.KB = 0; d.NF = 0; d.total = 0; d.R = 0; d.ndj = 0; d.nsj = 0; return; }
-  const int Tn = (j + TB - 1) / TB;
-  const int C = strip_len(j, G, P, upc);
-  d.Tn = Tn; d.C = C; d.rcpC = (65536 + C - 1) / C;
-  d.KB = (Tn - 1) / C;
-  d.NF = d.KB * Tn - C * (d.KB * (d.KB + 1) / 2);
-  d.total = d.NF + Tn;                 // P == 1 (P > 1: engine_prepare tabulates the owned units)
-  int R = (j + G - 1) / G;
-  d.R = (R + 7) & ~7;
-  const int Ij = (j - 1) / TB;         // tile row of the last row (row j' = j-1 of the following phase A)
-  d.ndj = Tn - (Ij + 1);
-  d.nsj = d.ndj + Ij / C + 1;
-}
-
 // ---- Householder scalars: LAPACK ?larfg without the safmin loop (zhetrd_gpu.F90:277-331, dsytrd_gpu.F90:408-443)
 __device__ __forceinline__ void larfg_scalars(double alpha, double xnorm2, double& beta, double& tau, double& scale) {
   if (xnorm2 == 0.0) { beta = alpha; tau = 0.0; scale = 1.0; return; }
@@ -295,68 +256,6 @@ __device__ __forceinline__ void larfg_scalars(double2 alpha, double xnorm2, doub
 // on) fetches it with TMA; 16 consumer warps follow the descriptors: warp w owns tile rows [4w, 4w+4), lane l owns
 // tile columns l and l+32.
 // =====================================================================================================
-struct UnitMap {
-  int Tn, C, rcpC, rank, P, TnO, KB, NF, total;
-  int keepI;            // tiles of tile rows < keepI are loaded with L2 evict_last, the others with evict_first (0: no hints)
-  const int* bstart;    // P > 1: bstart[k] = number of F units in bands < k (shared memory, KB+1 entries)
-  // owned tile columns are J = rank + P*jj, jj = 0..TnO-1
-  __device__ __forceinline__ int first_owned_at_least(int Jmin) const {   // smallest jj with rank + P*jj >= Jmin
-    const int d = Jmin - rank;
-    return d <= 0 ? 0 : (d + P - 1) / P;
-  }
-  __device__ __forceinline__ int band_count(int k) const {                // F units of band k
-    const int jj0 = first_owned_at_least((k + 1) * C);
-    return TnO - jj0 > 0 ? TnO - jj0 : 0;
-  }
-  // P == 1: F units before band k = k*Tn - C*k*(k+1)/2
-  __device__ __forceinline__ int prefix1(int k) const { return k * Tn - C * (k * (k + 1) / 2); }
-  // number of bands that have F units at all: (k+1)*C < Tn
-  __device__ __forceinline__ static int num_bands(int Tn_, int C_) { return Tn_ > 0 ? (Tn_ - 1) / C_ : 0; }
-  __device__ __forceinline__ void init(int n, int C_, int rank_, int P_, const int* bstart_) {
-    Tn = (n + TB - 1) / TB; C = C_; rcpC = (65536 + C_ - 1) / C_; rank = rank_; P = P_; bstart = bstart_; keepI = 0;
-    TnO = rank < Tn ? (Tn - rank + P - 1) / P : 0;
-    KB = num_bands(Tn, C);
-    NF = (P == 1) ? prefix1(KB) : (KB > 0 ? bstart[KB] : 0);
-    total = NF + TnO;
-  }
-  // tiles of a unit: off-diagonal (I, J) for I in [I0, I1), then the diagonal tile (J, J) when has_diag
-  __device__ __forceinline__ void decode(int unit, int& J, int& I0, int& I1, bool& has_diag) const {
-    if (unit < NF) {
-      int k;
-      if (P == 1) {
-        const double bq = (double)Tn - 0.5 * (double)C;
-        k = (int)((bq - sqrt(fmax(bq * bq - 2.0 * (double)C * (double)unit, 0.0))) / (double)C);
-        if (k < 0) k = 0;
-        if (k > KB - 1) k = KB - 1;
-        while (k > 0 && prefix1(k) > unit) --k;
-        while (k + 1 < KB && prefix1(k + 1) <= unit) ++k;
-        J = (k + 1) * C + (unit - prefix1(k));
-      } else {
-        int lo = 0, hi = KB - 1;                 // largest k with bstart[k] <= unit
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (bstart[mid] <= unit) lo = mid; else hi = mid - 1; }
-        k = lo;
-        J = rank + P * (first_owned_at_least((k + 1) * C) + (unit - bstart[k]));
-      }
-      I0 = k * C; I1 = k * C + C; has_diag = false;
-    } else {
-      int q = unit - NF;
-      if (P == 1) {
-        // decreasing size: a D unit has (J mod C) + 1 tiles; residue classes from the largest down
-        int s = (C < Tn ? C : Tn) - 1;
-        for (; s > 0; --s) {
-          const int cnt = (Tn - 1 - s) / C + 1;
-          if (q < cnt) break;
-          q -= cnt;
-        }
-        J = s + C * q;
-      } else {
-        J = rank + P * q;
-      }
-      I0 = (J / C) * C; I1 = J; has_diag = true;
-    }
-  }
-};
-
 __device__ __forceinline__ void ring_init(uint64_t* full, uint64_t* empty, int stages, RingState& rs) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
