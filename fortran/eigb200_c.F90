@@ -50,5 +50,22 @@ module eigb200_c
       type(c_ptr), value    :: work_h, rwork_h, iwork_h, Z_h, w_h
       integer(c_int)        :: info
     end function eigb200_zheevd
+
+    ! optional: stream the solver issues its work on / one-shot "A has been uploaded" event (include/eigb200.h)
+    integer(c_int) function eigb200_set_stream(stream) bind(C, name="eigb200_set_stream")
+      import :: c_int, cuda_stream_kind
+      integer(kind=cuda_stream_kind), value :: stream
+    end function eigb200_set_stream
+
+    integer(c_int) function eigb200_set_a_ready_event(ev) bind(C, name="eigb200_set_a_ready_event")
+      import :: c_int, cudaEvent
+      type(cudaEvent), value :: ev
+    end function eigb200_set_a_ready_event
+
+    integer(c_int) function eigb200_set_option(name, val) bind(C, name="eigb200_set_option")
+      import :: c_int, c_char
+      character(kind=c_char), dimension(*) :: name      ! null-terminated, e.g. "nvtx"//c_null_char
+      integer(c_int), value :: val
+    end function eigb200_set_option
   end interface
 end module eigb200_c
