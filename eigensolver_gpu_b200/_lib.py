@@ -28,6 +28,7 @@ SIGNATURES = {
     "eigb200_prof_reset": (_i, []),
     "eigb200_prof_collect": (_i, [_p, _p, _p]),
     "eigb200_trace_read": (C.c_longlong, [_p, C.c_longlong]),
+    "eigb200_probe_peaks": (_i, [_p]),
     "eigb200_set_option": (_i, [C.c_char_p, _i]),
     "eigb200_get_option": (_i, [C.c_char_p]),
     "eigb200_dsygvdx": (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _ip, _i]),
@@ -75,6 +76,15 @@ def load(strict=False):
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    return lib
+
+
+def sync_stream():
+    """Points the library at torch's CURRENT stream; every Python entry point calls this first, so that a call made
+    inside `with torch.cuda.stream(s)` and the next one made outside of it are each issued where the caller is."""
+    import torch
+    lib = load()
+    lib.eigb200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
     return lib
 
 

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import load
+from ._lib import load, sync_stream
 from . import stages as S
 
 
@@ -33,8 +33,7 @@ def _dp(t):
 
 
 def _sync_stream():
-    lib = load()
-    lib.eigb200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    sync_stream()
 
 
 def dsygvdx_gpu(N, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, work_h, lwork_h, iwork_h, liwork_h, Z_h, ldz_h, w_h,

@@ -67,6 +67,11 @@ long long eigb200_trace_read(unsigned long long* out, long long max_count) {
   return n;
 }
 
+int eigb200_probe_peaks(double* out4) {
+  API_BEGIN();
+  return probe_peaks(ctx().stream, out4);
+}
+
 int eigb200_set_option(const char* name, int value) { return set_option(name, value); }
 int eigb200_get_option(const char* name) { return get_option(name); }
 
@@ -115,7 +120,10 @@ int eigb200_dstedc(int n, double* d, double* e, double* Q, int ldq) {
   size_t need = stedc_scratch_bytes(n);
   void* scr = ctx_scratch(need);
   if (!scr) return -1;
-  return stedc_device(ctx().stream, n, d, e, Q, ldq, scr, ctx().scratch_bytes);
+  if (stedc_device(ctx().stream, n, d, e, Q, ldq, scr, ctx().scratch_bytes) != 0) return -1;
+  if (status_fetch(ctx().stream) != 0) return -1;
+  if (ctx().h_status[ST_STEDC] != 0) { set_last_error("dstedc: device status %d (1 QL, 2 secular, 3 non-finite)", ctx().h_status[ST_STEDC]); return -1; }
+  return 0;
 }
 
 int eigb200_dpotrf(int n, double* B, int ldb, int* info_h) {

@@ -92,8 +92,19 @@ struct Context {
   cudaEvent_t a_ready = nullptr;   // one-shot: the generalized driver waits for it before touching A
   void* scratch = nullptr;       // growable device scratch (stedc, panel partials, ...)
   size_t scratch_bytes = 0;
-  int* d_info = nullptr;         // device-side status words
+  int* d_info = nullptr;         // device-side status words: [0] hetrd watchdog, [1] potrf pivot, [2] stedc convergence
+  int* h_status = nullptr;       // pinned host mirror of d_info (read back once, at the end of a driver call)
+  int epoch = 0;                 // bumped whenever the device changes: per-device one-time setup (kernel attributes) is redone
   int verbose = 0;
+};
+// status word indices in Context::d_info
+enum StatusWord { ST_HETRD = 0, ST_POTRF = 1, ST_STEDC = 2, ST_NWORDS = 4 };
+// true exactly once per (call site, device epoch): guards cudaFuncSetAttribute-style per-device setup
+struct OncePerDevice {
+  int seen = -1;
+  bool need() { if (seen == ctx_epoch()) return false; return true; }
+  void done() { seen = ctx_epoch(); }
+  static int ctx_epoch();
 };
 Context& ctx();
 int ctx_init();

@@ -26,13 +26,23 @@ int ctx_init() {
   int dev = 0;
   EIGB_CUDA_CHECK(cudaGetDevice(&dev));
   if (c.initialized && c.device == dev) return 0;
-  if (c.initialized) {   // device changed: drop per-device resources
+  if (c.initialized) {
+    // device changed: release the old device's resources with that device current, then start over.  The caller's
+    // stream belonged to the old device as well: fall back to the legacy default stream until set_stream is called.
+    cudaSetDevice(c.device);
     if (c.scratch) cudaFree(c.scratch);
     c.scratch = nullptr; c.scratch_bytes = 0;
     if (c.d_info) cudaFree(c.d_info);
     c.d_info = nullptr;
+    if (c.stream2) cudaStreamDestroy(c.stream2);
+    if (c.ev1) cudaEventDestroy(c.ev1);
+    if (c.ev2) cudaEventDestroy(c.ev2);
     c.stream2 = nullptr; c.ev1 = c.ev2 = nullptr;
+    c.stream = 0; c.a_ready = nullptr;
+    c.initialized = false;
+    cudaSetDevice(dev);
   }
+  c.epoch += 1;
   cudaDeviceProp prop;
   EIGB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
   if (prop.major < 10) {
@@ -46,11 +56,14 @@ int ctx_init() {
   EIGB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev2, cudaEventDisableTiming));
   EIGB_CUDA_CHECK(cudaMalloc(&c.d_info, 64 * sizeof(int)));
   EIGB_CUDA_CHECK(cudaMemset(c.d_info, 0, 64 * sizeof(int)));
+  if (!c.h_status) EIGB_CUDA_CHECK(cudaHostAlloc((void**)&c.h_status, 64 * sizeof(int), cudaHostAllocPortable));
   const char* v = getenv("EIGB200_VERBOSE");
   c.verbose = v ? atoi(v) : 0;
   c.initialized = true;
   return 0;
 }
+
+int OncePerDevice::ctx_epoch() { return ctx().epoch; }
 
 void* ctx_scratch(size_t bytes) {
   Context& c = ctx();
@@ -126,6 +139,25 @@ void prof_collect(double* ms, int* cnt, long long* launches) {
   g_pairs.clear();
   for (int i = 0; i < PROF_NCAT; ++i) { ms[i] = g_ms[i]; cnt[i] = g_cnt[i]; }
   *launches = g_launches;
+}
+
+int status_fetch(cudaStream_t s) {
+  Context& c = ctx();
+  EIGB_CUDA_CHECK(cudaMemcpyAsync(c.h_status, c.d_info, ST_NWORDS * sizeof(int), cudaMemcpyDeviceToHost, s));
+  EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return 0;
+}
+int status_check(const char* who, int* potrf_pivot) {
+  const int* h = ctx().h_status;
+  if (potrf_pivot) *potrf_pivot = h[ST_POTRF];
+  if (h[ST_POTRF] != 0) { set_last_error("%s error: potrf failed (B not positive definite at pivot %d)", who, h[ST_POTRF]); return -1; }
+  if (h[ST_HETRD] != 0) { set_last_error("%s error: hetrd device status %d (grid barrier / exchange watchdog)", who, h[ST_HETRD]); return -1; }
+  if (h[ST_STEDC] != 0) {
+    set_last_error("%s error: stedc failed (%s)", who, h[ST_STEDC] == 1 ? "leaf QL iteration did not converge" :
+                   h[ST_STEDC] == 2 ? "secular equation did not converge" : "non-finite eigenvalue");
+    return -1;
+  }
+  return 0;
 }
 
 Options& opts() { static Options o; return o; }

@@ -30,7 +30,7 @@ template <typename T>
 int heevd_core(cudaStream_t s, int n, int il, int iu, T* A, int64_t lda, T* Z, int64_t ldz, double* w, double* d_e,
                T* d_tau, const T* restore_from, int64_t ld_restore) {
   const int m = iu - il + 1;
-  if (hetrd_upper<T>(s, n, A, lda, w, d_e, d_tau) != 0) return -1;
+  if (hetrd_upper<T>(s, n, A, lda, w, d_e, d_tau, /*sync_status=*/false) != 0) return -1;
   if (restore_from) {
     if (restore_lower<T>(s, n, A, lda, restore_from, ld_restore) != 0) return -1;
   }
@@ -57,9 +57,19 @@ int copy_results_to_host(cudaStream_t s, int n, int m, const T* Z, int64_t ldz, 
     EIGB_CUDA_CHECK(cudaMemcpy2DAsync(Z_h, (size_t)ldz_h * sizeof(T), Z, (size_t)ldz * sizeof(T), (size_t)n * sizeof(T),
                                       m, cudaMemcpyDeviceToHost, s));
   }
-  EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
-  return 0;
+  return status_fetch(s);      // (stream synchronisation inside)
 }
+
+// every early return of a driver reports through *info as well (the reference's only error channel)
+#define EIGB_DRV_CHECK(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      set_last_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      *info = -1;                                                                              \
+      return -1;                                                                               \
+    }                                                                                          \
+  } while (0)
 
 template <typename T>
 int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, int iu, double* w, T* work, int lwork,
@@ -79,12 +89,14 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
     if (lwork < 2 * 64 * 64 + 65 * N) msg = "lwork must be at least 2*64*64 + 65*N";
     else if (lrwork < N) msg = "lrwork must be at least N";
     else if (lwork_h < N) msg = "lwork_h must be at least N";
-    else if (lrwork_h >= 0 && lrwork_h < 1 + 5 * N + 2 * N * N && 1 + 5 * N + 2 * N * N <= 2147483647LL)
+    // (when the formula exceeds a default integer the caller cannot state it -- N >= 32767 -- and the host
+    // workspace is unused here anyway: accept whatever was passed, including an overflowed negative value)
+    else if (1 + 5 * N + 2 * N * N <= 2147483647LL && lrwork_h < 1 + 5 * N + 2 * N * N)
       msg = "lrwork_h must be at least 1 + 5*N + 2*N*N";
     else if (liwork_h < N) msg = "liwork_h must be at least 3 + 5*N";
   } else {
     if (lwork < 2 * 64 * 64 + 66 * N) msg = "lwork must be at least 2*64*64 + 66*N";
-    else if (lwork_h >= 0 && lwork_h < 1 + 6 * N + 2 * N * N && 1 + 6 * N + 2 * N * N <= 2147483647LL)
+    else if (1 + 6 * N + 2 * N * N <= 2147483647LL && lwork_h < 1 + 6 * N + 2 * N * N)
       msg = "lwork_h must be at least 1 + 6*N + 2*N*N";
     else if (liwork_h < N) msg = "liwork_h must be at least 3 + 5*N";
   }
@@ -99,19 +111,20 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
   if (n == 0) return 0;
   cudaStream_t s = ctx().stream;
   const int m = iu - il + 1;
-  int pinfo = 0;
+  // The pivot status of the factorization stays on the device and is read back with the final synchronisation of the
+  // call (the reference blocks on devInfo right here, zhegvdx_gpu.F90:136-141): nothing below can hang on a failed
+  // factorization -- every device loop is bounded -- and the host keeps enqueueing work meanwhile.
   prof_begin(PROF_POTRF, s);
-  int prc = potrf_upper<T>(s, n, B, ldb, &pinfo);
+  int prc = potrf_upper<T>(s, n, B, ldb, nullptr, /*sync_status=*/false);
   prof_end(PROF_POTRF, s);
-  if (prc != 0 || pinfo != 0) {
+  if (prc != 0) {
     printf(" %s error: potrf failed!\n", name);
-    if (pinfo != 0) set_last_error("%s error: potrf failed (B not positive definite at pivot %d)", name, pinfo);
     *info = -1;
     return -1;
   }
   // a caller that uploads A asynchronously on another stream while B is being factored hands over the event of
   // that copy (eigb200_set_a_ready_event, one-shot): wait for it before A is touched
-  if (a_ready != nullptr) EIGB_CUDA_CHECK(cudaStreamWaitEvent(s, a_ready, 0));
+  if (a_ready != nullptr) EIGB_DRV_CHECK(cudaStreamWaitEvent(s, a_ready, 0));
   // tril(A) -> Z, A <- U^-H A U^-1 (zhegvdx_gpu.F90:145-158)
   prof_begin(PROF_HEGST, s);
   int hrc = hegst_upper<T>(s, n, A, lda, B, ldb, Z, ldz);
@@ -143,8 +156,7 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
       trc = trsm_upper<T>(s, 'L', 'N', n, mc, B, ldb, Z + (int64_t)c0 * ldz, ldz);
       if (trc != 0) break;
       if (cudaEventCreateWithFlags(&evs[ne], cudaEventDisableTiming) != cudaSuccess) { trc = -1; break; }
-      cudaEventRecord(evs[ne], s);
-      cudaStreamWaitEvent(c.stream2, evs[ne], 0);
+      if (cudaEventRecord(evs[ne], s) != cudaSuccess || cudaStreamWaitEvent(c.stream2, evs[ne], 0) != cudaSuccess) { trc = -1; break; }
       if (cudaMemcpy2DAsync(Z_h + (int64_t)c0 * ldz_h, (size_t)ldz_h * sizeof(T), Z + (int64_t)c0 * ldz,
                             (size_t)ldz * sizeof(T), (size_t)n * sizeof(T), mc, cudaMemcpyDeviceToHost, c.stream2)
           != cudaSuccess) trc = -1;
@@ -153,13 +165,15 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
     if (trc == 0 && w_h) {
       if (cudaMemcpyAsync(w_h, w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) trc = -1;
     }
-    cudaError_t e1 = cudaStreamSynchronize(c.stream2), e2 = cudaStreamSynchronize(s);
+    cudaError_t e1 = cudaStreamSynchronize(c.stream2);
+    const int e2 = status_fetch(s);
     for (int i = 0; i < 8; ++i) if (evs[i]) cudaEventDestroy(evs[i]);
-    if (trc != 0 || e1 != cudaSuccess || e2 != cudaSuccess) {
+    if (trc != 0 || e1 != cudaSuccess || e2 != 0) {
       printf(" %s error: solve with U / copy to host failed!\n", name);
       *info = -1;
       return -1;
     }
+    if (status_check(name) != 0) { printf(" %s error: %s\n", name, "see eigb200_last_error()"); *info = -1; return -1; }
     return 0;
   }
   trc = trsm_upper<T>(s, 'L', 'N', n, m, B, ldb, Z, ldz);
@@ -170,6 +184,7 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
     *info = -1;
     return -1;
   }
+  if (status_check(name) != 0) { printf(" %s error: %s\n", name, "see eigb200_last_error()"); *info = -1; return -1; }
   return 0;
 }
 
@@ -178,6 +193,7 @@ int heevd_driver(int il, int iu, int n, T* A, int lda, T* Z, int ldz, double* w,
                  int lrwork, T* Z_h, int ldz_h, double* w_h, int* info) {
   const bool cplx = is_cplx<T>::value;
   *info = 0;
+  ctx().a_ready = nullptr;       // one-shot event of the generalized driver: never left armed
   const int64_t N = n;
   const char* name = cplx ? "zheevd_gpu" : "dsyevd_gpu";
   const char* msg = nullptr;
@@ -200,7 +216,9 @@ int heevd_driver(int il, int iu, int n, T* A, int lda, T* Z, int ldz, double* w,
   double* d_e = cplx ? rwork : reinterpret_cast<double*>(work);
   T* d_tau = cplx ? work : work + n;
   if (heevd_core<T>(s, n, il, iu, A, lda, Z, ldz, w, d_e, d_tau, (const T*)nullptr, 0) != 0) { *info = -1; return -1; }
+  EIGB_DRV_CHECK(cudaMemsetAsync(ctx().d_info + ST_POTRF, 0, sizeof(int), s));
   if (copy_results_to_host<T>(s, n, iu - il + 1, Z, ldz, w, Z_h, ldz_h, w_h, false) != 0) { *info = -1; return -1; }
+  if (status_check(name) != 0) { printf(" %s error: %s\n", name, "see eigb200_last_error()"); *info = -1; return -1; }
   return 0;
 }
 

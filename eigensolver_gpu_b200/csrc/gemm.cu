@@ -240,11 +240,11 @@ int launch_one(cudaStream_t s, const GemmParams<T>& p, const GemmParams<T>* dev,
   constexpr int A_ELEMS = AK ? C_::BM * (BKT + KPAD) : BKT * (C_::BM + C_::PAD);
   constexpr int B_ELEMS = BK ? C_::BN * (BKT + KPAD) : BKT * (C_::BN + C_::PAD);
   constexpr int SMEM = num_stages_<T, AK, BK>() * (A_ELEMS + B_ELEMS) * (int)sizeof(T);
-  static bool attr_set = false;
+  static OncePerDevice once;
   auto kern = gemm_kernel<T, AK, BK, CH>;
-  if (!attr_set) {
+  if (once.need()) {
     EIGB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
+    once.done();
   }
   int M = dev ? maxM : p.M, N = dev ? maxN : p.N;
   if (M <= 0 || N <= 0) return 0;

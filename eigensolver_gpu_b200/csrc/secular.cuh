@@ -8,7 +8,8 @@
 // Problem: roots of f(x) = 1/rho + sum_i z_i^2 / (d_i - x), d ascending, rho > 0, z_i != 0.
 // Root j lies in (d_j, d_{j+1}) for j < k-1 and in (d_{k-1}, d_{k-1} + rho*||z||^2) for j = k-1.
 // Output: the origin index K (the nearer pole) and tau with  lambda_j = d_K + tau;  the caller forms the
-// differences d_i - lambda_j = (d_i - d_K) - tau without cancellation.
+// differences d_i - lambda_j = (d_i - d_K) - tau without cancellation.  iters_out > 80 reports non-convergence
+// (dlaed4 would return info = 1; zheevd_gpu.F90:102-106 turns that into info = -1).
 //
 // The sums over i are supplied by an Evaluator so that the same control flow runs serially on the host
 // (unit tests against dlaed4) and warp-cooperatively on the device (every lane executes the identical
@@ -33,7 +34,7 @@ struct SecularSums {
 template <class Evaluator>
 EIGB_HD void secular_root(int k, int j, const double* d, const double* z, double rho, double znorm2, Evaluator ev,
                           int& Kout, double& tau_out, int& iters_out) {
-  const double eps = 2.220446049250313e-16;
+  const double eps = 1.1102230246251565e-16;       // LAPACK dlamch('Epsilon') (relative rounding unit), as dlaed4
   const double rhoinv = 1.0 / rho;
   iters_out = 0;
   if (k == 1) { Kout = 0; tau_out = rho * z[0] * z[0]; return; }
@@ -98,6 +99,7 @@ EIGB_HD void secular_root(int k, int j, const double* d, const double* z, double
     if (!(tnew > lo && tnew < hi)) tnew = 0.5 * (lo + hi);   // bisection safeguard
     if (tnew == tau) break;
     tau = tnew;
+    if (it == MAXIT - 1) iters_out = MAXIT + 1;      // ran out of iterations without meeting a stopping test
   }
   Kout = K; tau_out = tau;
 }

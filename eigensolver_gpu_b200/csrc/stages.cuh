@@ -45,7 +45,14 @@ std::vector<unsigned long long>& trace_store();
 // y = A x (A Hermitian, upper triangle read), deterministic tile reduction
 template <typename T> int hemv_upper(cudaStream_t s, int n, const T* A, int64_t lda, const T* x, T* y);
 // blocked tridiagonalization, UPLO='U'
-template <typename T> int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, T* tau);
+// sync_status = false: the watchdog status word stays in ctx().d_info[ST_HETRD] for the caller's final status_fetch
+template <typename T> int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, T* tau, bool sync_status = true);
+// copies the device status words to the pinned host mirror and synchronises the stream; then status_check() turns
+// them into the reference's info convention (0 ok, -1 + message)
+int status_fetch(cudaStream_t s);
+// live peak probes (probe.cu): out[0] DMMA TFLOP/s, out[1] DFMA TFLOP/s, out[2] HBM read GB/s, out[3] HBM copy GB/s
+int probe_peaks(cudaStream_t s, double* out);
+int status_check(const char* who, int* potrf_pivot = nullptr);
 
 // tridiagonal divide & conquer on the device
 size_t stedc_scratch_bytes(int n);
@@ -55,7 +62,8 @@ int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t
 // Cholesky / triangular solves / reduction to standard form (trsm.cu)
 template <typename T> int symmetrize_from_upper(cudaStream_t s, int n, T* A, int64_t lda, T* save, int64_t lds);
 template <typename T> int restore_lower(cudaStream_t s, int n, T* A, int64_t lda, const T* save, int64_t lds);
-template <typename T> int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h);
+// sync_status = false: *info_h is not written, the pivot index stays in ctx().d_info[ST_POTRF]
+template <typename T> int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h, bool sync_status = true);
 template <typename T>
 int trsm_upper(cudaStream_t s, char side, char trans, int m, int n, const T* U, int64_t ldu, T* B, int64_t ldb);
 template <typename T>

@@ -23,7 +23,8 @@ namespace eigb200 {
 namespace {
 
 constexpr int LEAF = 32;
-constexpr double DC_EPS = 2.220446049250313e-16;
+constexpr double QL_EPS = 2.220446049250313e-16;    // leaf QL iteration: EISPACK tql2's machine epsilon
+constexpr double DC_EPS = 1.1102230246251565e-16;   // deflation: LAPACK dlamch('Epsilon'), as dlaed2
 
 __host__ __device__ __forceinline__ int leaf_bound(int i, int n, int L) { return (int)(((long long)i * n) / L); }
 
@@ -38,6 +39,7 @@ struct DcWork {
   int *idx, *typ, *srccol, *posg, *cmap, *dstcol, *rotp, *rotn, *permnd, *permdf;
   int *K;               // per merge: k, k1, k2, k3, nrot  (5 ints per merge)
   GemmParams<double>* gp;
+  int* status;          // device status word: 1 leaf QL did not converge, 2 secular equation, 3 non-finite eigenvalue
 };
 
 struct MergeGeom { int lo, n1, n2, n; };
@@ -55,10 +57,13 @@ __device__ __forceinline__ MergeGeom merge_geom(const DcWork& w, int level, int 
 __global__ void dc_scale_kernel(DcWork w) {
   __shared__ double red[32];
   double mx = 0.0;
+  bool bad = false;
   for (int i = threadIdx.x; i < w.n; i += blockDim.x) {
     mx = fmax(mx, fabs(w.D[i]));
-    if (i < w.n - 1) mx = fmax(mx, fabs(w.E[i]));
+    bad |= !isfinite(w.D[i]);
+    if (i < w.n - 1) { mx = fmax(mx, fabs(w.E[i])); bad |= !isfinite(w.E[i]); }
   }
+  if (bad) atomicMax(w.status, 3);            // NaN/Inf in T: comparisons below would silently drop it
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
@@ -74,7 +79,11 @@ __global__ void dc_scale_kernel(DcWork w) {
 }
 __global__ void dc_unscale_kernel(DcWork w) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < w.n) w.D[i] *= w.scale[0];
+  if (i < w.n) {
+    const double v = w.D[i] * w.scale[0];
+    w.D[i] = v;
+    if (!isfinite(v)) atomicMax(w.status, 3);
+  }
 }
 
 // ---- leaves: implicit QL with eigenvectors (EISPACK tql2 recurrence), one warp per leaf -----------------
@@ -102,7 +111,7 @@ __global__ void __launch_bounds__(128) dc_leaf_kernel(DcWork w) {
   for (int l = 0; l < n; ++l) {
     tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
     int m = l;
-    while (m < n - 1) { if (fabs(e[m]) <= DC_EPS * tst1) break; ++m; }
+    while (m < n - 1) { if (fabs(e[m]) <= QL_EPS * tst1) break; ++m; }
     if (m > l) {
       int iter = 0;
       bool again;
@@ -145,7 +154,8 @@ __global__ void __launch_bounds__(128) dc_leaf_kernel(DcWork w) {
         __syncwarp();
         e[l] = s * p; d[l] = c * p;
         __syncwarp();
-        again = fabs(e[l]) > DC_EPS * tst1 && iter < 60;
+        again = fabs(e[l]) > QL_EPS * tst1;
+        if (again && iter >= 60) { again = false; if (lane == 0) atomicMax(w.status, 1); }   // ?steql's 30*n limit
         __syncwarp();
       } while (again);
     }
@@ -359,6 +369,7 @@ __global__ void __launch_bounds__(256) dc_secular_kernel(DcWork w, int level) {
   WarpSecularEval ev{k, j, lane, d, z};
   int Ko, it; double tau;
   secular_root(k, j, d, z, rho, zn2, ev, Ko, tau, it);
+  if (it > 80 && lane == 0) atomicMax(w.status, 2);
   const double dK = d[Ko];
   if (lane == 0) w.Dnew[g.lo + j] = dK + tau;
   const int* posg = w.posg + g.lo;
@@ -451,6 +462,7 @@ size_t stedc_scratch_bytes(int n) {
 int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t ldq, void* scratch,
                  size_t scratch_bytes) {
   if (n <= 0) return 0;
+  EIGB_CUDA_CHECK(cudaMemsetAsync(ctx().d_info + ST_STEDC, 0, sizeof(int), s));
   EIGB_CUDA_CHECK(cudaMemset2DAsync(Q, ldq * sizeof(double), 0, (size_t)n * sizeof(double), n, s));
   if (n == 1) {
     dc_identity_kernel<<<1, 32, 0, s>>>(Q, ldq, 1);
@@ -477,17 +489,18 @@ int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t
   w.K = ar.take<int>(5 * (size_t)(n / 2 + 2));
   w.gp = ar.take<GemmParams<double>>(2 * (size_t)(n / 2 + 2));
   if (!w.gp) { set_last_error("stedc: scratch arena exhausted"); return -1; }
+  w.status = ctx().d_info + ST_STEDC;
 
   ProfScope ps(PROF_STEDC, s);
   dc_scale_kernel<<<1, 1024, 0, s>>>(w);
   count_launch(1);
   dc_leaf_kernel<<<cdiv(w.L, 4), 128, 0, s>>>(w);
   EIGB_LAUNCH_CHECK();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static OncePerDevice once;
+  if (once.need()) {
     EIGB_CUDA_CHECK(cudaFuncSetAttribute(dc_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          DEFL_SMEM_ELEMS * 16));
-    attr_set = true;
+    once.done();
   }
   for (int level = 1; level <= levels; ++level) {
     const int nmerge = w.L >> level;

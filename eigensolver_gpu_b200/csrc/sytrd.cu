@@ -1206,13 +1206,13 @@ __global__ void __launch_bounds__(NTT, 1) phase_b_kernel(const __grid_constant__
 
 template <typename T>
 int panel_grid(int& grid, size_t dyn_smem) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static OncePerDevice once;
+  if (once.need()) {
     EIGB_CUDA_CHECK(cudaFuncSetAttribute(panel_coop_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
     EIGB_CUDA_CHECK(cudaFuncSetAttribute(panel_coop_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
     EIGB_CUDA_CHECK(cudaFuncSetAttribute(phase_b_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
     EIGB_CUDA_CHECK(cudaFuncSetAttribute(hemv_tiles_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes<T>()));
-    attr_set = true;
+    once.done();
   }
   int per_sm = 0;
   EIGB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_coop_kernel<T, true>, NTT, dyn_smem));
@@ -1270,7 +1270,7 @@ int hemv_upper(cudaStream_t s, int n, const T* A, int64_t lda, const T* x, T* y)
 // On exit the reflectors v_j (j = 1..n-1, 1-based) are in A(1:j-1, j+1) with the unit element stored
 // explicitly, exactly as the reference leaves them (zhetrd_gpu.F90:92).
 template <typename T>
-int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, T* tau) {
+int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, T* tau, bool sync_status) {
   if (n <= 0) return 0;
   Context& c = ctx();
   const int nb = opts().trd_nb < NBMAX ? opts().trd_nb : NBMAX;
@@ -1430,8 +1430,10 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     hi = p.i0;
   }
   int st = 0;
-  EIGB_CUDA_CHECK(cudaMemcpyAsync(&st, p.status, sizeof(int), cudaMemcpyDeviceToHost, s));
-  EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (sync_status || p.trace) {
+    EIGB_CUDA_CHECK(cudaMemcpyAsync(&st, p.status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
   if (p.trace) {
     trace_store().resize((size_t)n * TRSLOTS + 1024);
     cudaMemcpy(trace_store().data(), p.trace, ((size_t)n * TRSLOTS + 1024) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -1443,7 +1445,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
 
 template int hemv_upper<double>(cudaStream_t, int, const double*, int64_t, const double*, double*);
 template int hemv_upper<double2>(cudaStream_t, int, const double2*, int64_t, const double2*, double2*);
-template int hetrd_upper<double>(cudaStream_t, int, double*, int64_t, double*, double*, double*);
-template int hetrd_upper<double2>(cudaStream_t, int, double2*, int64_t, double*, double*, double2*);
+template int hetrd_upper<double>(cudaStream_t, int, double*, int64_t, double*, double*, double*, bool);
+template int hetrd_upper<double2>(cudaStream_t, int, double2*, int64_t, double*, double*, double2*, bool);
 
 }  // namespace eigb200

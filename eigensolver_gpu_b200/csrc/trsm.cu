@@ -209,8 +209,8 @@ int enable_smem(K kern, size_t bytes) {
 }
 template <typename T>
 int enable_all_smem() {
-  static bool done = false;
-  if (done) return 0;
+  static OncePerDevice once;
+  if (!once.need()) return 0;
   if (enable_smem(trtri_blocks_kernel<T>, tri_smem<T>()) != 0) return -1;
   if (enable_smem(potf2_block_kernel<T>, tri_smem<T>()) != 0) return -1;
   if (enable_smem(diag_mult_kernel<T, true, true, 64>, blk_smem<T>()) != 0) return -1;
@@ -219,7 +219,7 @@ int enable_all_smem() {
   if (enable_smem(diag_mult_kernel<T, true, true, 16>, blk_smem<T>()) != 0) return -1;
   if (enable_smem(diag_mult_kernel<T, true, false, 16>, blk_smem<T>()) != 0) return -1;
   if (enable_smem(diag_mult_kernel<T, false, false, 16>, blk_smem<T>()) != 0) return -1;
-  done = true;
+  once.done();
   return 0;
 }
 
@@ -453,8 +453,8 @@ int potrf_rec(cudaStream_t s, int lo, int hi, T* A, int64_t lda, T* Dinv, int* d
 
 // Cholesky B = U^H U (upper, in place).  *info_h = 0 or the 1-based index of the first non-positive pivot.
 template <typename T>
-int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h) {
-  *info_h = 0;
+int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h, bool sync_status) {
+  if (sync_status) *info_h = 0;
   if (n <= 0) return 0;
   if (enable_all_smem<T>() != 0) return -1;
   Context& c = ctx();
@@ -465,8 +465,10 @@ int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h) {
   int* dinfo = c.d_info + 1;
   EIGB_CUDA_CHECK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
   if (potrf_rec<T>(s, 0, n, B, ldb, Dinv, dinfo) != 0) return -1;
-  EIGB_CUDA_CHECK(cudaMemcpyAsync(info_h, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
-  EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (sync_status) {
+    EIGB_CUDA_CHECK(cudaMemcpyAsync(info_h, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+    EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
   return 0;
 }
 
@@ -532,7 +534,7 @@ int hegst_upper(cudaStream_t s, int n, T* A, int64_t lda, const T* U, int64_t ld
 #define EIGB_INST(T)                                                                                     \
   template int symmetrize_from_upper<T>(cudaStream_t, int, T*, int64_t, T*, int64_t);                    \
   template int restore_lower<T>(cudaStream_t, int, T*, int64_t, const T*, int64_t);                      \
-  template int potrf_upper<T>(cudaStream_t, int, T*, int64_t, int*);                                     \
+  template int potrf_upper<T>(cudaStream_t, int, T*, int64_t, int*, bool);                                  \
   template int trsm_upper<T>(cudaStream_t, char, char, int, int, const T*, int64_t, T*, int64_t);        \
   template int hegst_upper<T>(cudaStream_t, int, T*, int64_t, const T*, int64_t, T*, int64_t);
 EIGB_INST(double)

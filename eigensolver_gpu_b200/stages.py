@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import check, load
+from ._lib import check, sync_stream as load     # every stage call is issued on torch's current stream
 
 
 def to_dev(a, device="cuda"):

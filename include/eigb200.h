@@ -55,6 +55,10 @@ int eigb200_prof_enable(int on);
 int eigb200_prof_reset(void);
 int eigb200_prof_collect(double* ms, int* cnt, long long* launches);
 
+/* live peak probes for the roofline denominators (about 0.3 s): out4[0] FP64 tensor (DMMA m8n8k4) TFLOP/s, out4[1] FP64 FMA
+ * TFLOP/s, out4[2] HBM read-only GB/s, out4[3] HBM copy GB/s (read + write bytes); no reference analogue */
+int eigb200_probe_peaks(double* out4);
+
 /* profiling aid: with option "trd_trace"=1 the tridiagonalization records 16 globaltimer stamps (ns) per column
  * (slots 0-4: phase A start/end, after barrier, phase B end, after barrier; 5-13: finer steps inside the phases,
  * see tools/trace_hetrd.py); read them back here. Returns the count. */

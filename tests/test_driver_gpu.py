@@ -97,6 +97,7 @@ def test_workspace_errors_follow_reference():
     assert args(lwork_h=n - 1) == -1
     assert args(lrwork_h=5 * n + 2 * n * n) == -1
     assert args(liwork_h=n - 1) == -1
+    assert args(lrwork_h=-5) == -1 and args(lwork_h=-1) == -1 and args(liwork_h=-3) == -1     # negative lengths are rejected
     wsd = api.Workspace(n, False)
     ad = torch.eye(n, dtype=torch.float64, device="cuda")
     bd = torch.eye(n, dtype=torch.float64, device="cuda")
@@ -104,6 +105,47 @@ def test_workspace_errors_follow_reference():
                            wsd.liwork_h, None, n, wsd.w_h, True) == -1
     assert api.dsygvdx_gpu(n, ad, n, bd, n, wsd.Z, n, 1, n, wsd.w, wsd.work, wsd.lwork, None, wsd.lwork_h - 1, None,
                            wsd.liwork_h, None, n, wsd.w_h, True) == -1
+
+
+def test_negative_host_workspace_real():
+    from eigensolver_gpu_b200 import api
+    n = 64
+    wsd = api.Workspace(n, False)
+    ad = torch.eye(n, dtype=torch.float64, device="cuda")
+    bd = torch.eye(n, dtype=torch.float64, device="cuda")
+    assert api.dsygvdx_gpu(n, ad, n, bd, n, wsd.Z, n, 1, n, wsd.w, wsd.work, wsd.lwork, None, -7, None,
+                           wsd.liwork_h, None, n, wsd.w_h, True) == -1
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_nvtx_ranges_option(level):
+    """option "nvtx" (the nvtx_inters counterpart, toolbox.F90:25-99): 1 = range per stage, 2 = with the reference's stream
+    synchronisation at both ends; results must not depend on it"""
+    from eigensolver_gpu_b200._lib import load
+    lib = load()
+    a, b = matgen.family_c(260, True, seed=3)
+    info0, w0, z0, *_ = _solve(a, b, 1, 100, skip=True)
+    assert lib.eigb200_set_option(b"nvtx", level) == 0 and lib.eigb200_get_option(b"nvtx") == level
+    try:
+        info, w, z, *_ = _solve(a, b, 1, 100, skip=True)
+    finally:
+        lib.eigb200_set_option(b"nvtx", 0)
+    assert info0 == 0 and info == 0
+    assert np.array_equal(w, w0) and np.array_equal(z, z0)
+
+
+def test_stedc_failure_is_reported():
+    """non-finite tridiagonal input: the device status word turns into an error return (the reference returns info = -1
+    when ?stedc fails, zheevd_gpu.F90:102-106) instead of a silent info = 0"""
+    from eigensolver_gpu_b200 import stages as S
+    from eigensolver_gpu_b200._lib import Eigb200Error
+    d = torch.ones(200, dtype=torch.float64, device="cuda")
+    e = torch.ones(199, dtype=torch.float64, device="cuda")
+    d[17] = float("nan")
+    with pytest.raises(Eigb200Error):
+        S.stedc(d, e)
+    w, q = S.stedc(torch.ones(200, dtype=torch.float64, device="cuda"), e)      # and the status word is reset afterwards
+    assert bool(torch.isfinite(w).all())
 
 
 def test_not_positive_definite_b_returns_minus_one():

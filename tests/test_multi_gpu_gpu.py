@@ -1,4 +1,9 @@
-"""2-GPU test of the distributed driver (skipped unless >= 2 CUDA devices): NCCL ranks spawned from the test."""
+"""Multi-GPU tests of the distributed driver (skipped unless enough CUDA devices): NCCL ranks spawned from the test.
+
+The in-kernel exchange variant of the panel kernel (`panel_coop_kernel<T, true>` + the peer-memory exchange) must
+actually run: the workers force the distributed tridiagonalization whatever the order (`dist_hetrd_min_n = 0`) and lower
+`mg_switch_n` so that the exchange stays on down to a trailing order of 256 (with the defaults the
+committed orders never reached that kernel)."""
 import os
 import socket
 
@@ -11,6 +16,14 @@ from oracle import lapack, matgen, metrics
 pytestmark = pytest.mark.gpu
 
 
+def _force_distributed(MG):
+    from eigensolver_gpu_b200._lib import load
+    assert load().eigb200_set_option(b"mg_switch_n", 256) == 0
+    be = MG.CudaStages()
+    be.dist_hetrd_min_n = lambda world: 0
+    return be
+
+
 def _worker(rank, world, port, cplx, n, il, iu, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -19,29 +32,34 @@ def _worker(rank, world, port, cplx, n, il, iu, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from eigensolver_gpu_b200 import multi_gpu as MG, stages as S
     a, b = matgen.family_c(n, cplx, seed=5)
-    info, w, z = MG.hegvdx_distributed(S.to_dev(np.triu(a)), S.to_dev(np.triu(b)), il, iu)
+    info, w, z = MG.hegvdx_distributed(S.to_dev(np.triu(a)), S.to_dev(np.triu(b)), il, iu, backend=_force_distributed(MG))
     if rank == 0:
         out.put((info, S.to_host(w).copy(), np.array(S.to_host(z))))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cplx", [False, True])
-def test_distributed_solve_two_gpus(cplx):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def _spawn(target, world, args, timeout=600):
     import torch.multiprocessing as mp
-    n, il, iu = 700, 1, 300
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, cplx, n, il, iu, q)) for r in range(2)]
+    procs = [ctx.Process(target=target, args=(r, world, port) + args + (q,)) for r in range(world)]
     for p in procs:
         p.start()
-    info, w, z = q.get(timeout=300)
+    res = q.get(timeout=timeout)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("cplx,n,il,iu", [(False, 700, 1, 300), (True, 700, 1, 300), (True, 2500, 1, 2500), (False, 3000, 1, 400)])
+def test_distributed_solve(world, cplx, n, il, iu):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    info, w, z = _spawn(_worker, world, (cplx, n, il, iu))
     a, b = matgen.family_c(n, cplx, seed=5)
     wr, zr, ur, linfo = lapack.hegvd(a, b)
     assert info == 0
@@ -58,39 +76,38 @@ def _worker_hetrd(rank, world, port, cplx, n, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from eigensolver_gpu_b200 import multi_gpu as MG, stages as S
     a, _ = matgen.family_c(n, cplx, seed=8)
-    be = MG.CudaStages()
-    be.dist_hetrd_min_n = lambda world: 0          # force the distributed tridiagonalization
+    be = _force_distributed(MG)
     ad = S.to_dev(np.triu(a))
     d, e, tau = be.hetrd_dist(ad)
     ds = [torch.zeros_like(d) for _ in range(world)]
     dist.all_gather(ds, d)
     same = all(torch.equal(ds[0], x) for x in ds)
+    # single-GPU result of the same input on rank 0 (the replicated kernel) for a direct comparison
+    d1 = e1 = None
     if rank == 0:
-        out.put((S.to_host(d).copy(), S.to_host(e).copy(), same))
+        be._ex.close()
+        a1 = S.to_dev(np.triu(a))
+        d1, e1, _ = S.hetrd(a1)
+        out.put((S.to_host(d).copy(), S.to_host(e).copy(), same, S.to_host(d1).copy(), S.to_host(e1).copy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cplx", [False, True])
-def test_distributed_tridiagonalization_two_gpus(cplx):
-    """1-D block-cyclic trailing matrix + in-kernel peer exchange: same (d, e) as LAPACK, bitwise equal on all ranks"""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    n = 1300
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    procs = [ctx.Process(target=_worker_hetrd, args=(r, 2, port, cplx, n, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    d, e, same = q.get(timeout=300)
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("cplx,n", [(False, 1300), (True, 1300), (True, 4500)])
+def test_distributed_tridiagonalization(world, cplx, n):
+    """1-D block-cyclic trailing matrix + in-kernel peer exchange: same (d, e) as LAPACK and as the single-GPU kernel,
+    bitwise equal on all ranks"""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    d, e, same, d1, e1 = _spawn(_worker_hetrd, world, (cplx, n))
     a, _ = matgen.family_c(n, cplx, seed=8)
-    _, dl, el, _ = lapack.hetrd(a)
     an = np.abs(a).sum(axis=0).max()
     assert same
-    assert np.abs(d - dl).max() <= 20 * n * metrics.EPS * an
-    assert np.abs(e - el).max() <= 20 * n * metrics.EPS * an
+    assert np.isfinite(d).all() and np.isfinite(e).all()
+    assert np.abs(d - d1).max() <= 20 * n * metrics.EPS * an
+    assert np.abs(np.abs(e) - np.abs(e1)).max() <= 20 * n * metrics.EPS * an
+    if n <= 2000:
+        _, dl, el, _ = lapack.hetrd(a)
+        assert np.abs(d - dl).max() <= 20 * n * metrics.EPS * an
+        assert np.abs(e - el).max() <= 20 * n * metrics.EPS * an
