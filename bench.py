@@ -121,9 +121,10 @@ def workload_config(args):
             "inputs": "family R (reference recipe A=T*T^H, B=T*T^H), seed 1234 (same problem on every rank)",
             "l2": "inputs (N^2*16 B each) larger than the 126 MB L2; A,B restored from pristine device copies "
                   "inside the timed region (2 D2D copies per step)",
-            "parallelism": ("1 problem over %d GPUs: hegst solves, back-transform and final trsm split by columns (NCCL "
-                            "exchanges); hetrd trailing matrix 1-D block-cyclic with in-kernel NVLink exchange; "
-                            "potrf/stedc replicated (bitwise deterministic)" % args.gpus)
+            "parallelism": ("1 problem over %d GPUs through eigb200_zhegvdx_mg/dsygvdx_mg (C ABI, library-owned NCCL "
+                            "communicator): hegst solves, back-transform and final trsm split by columns (NCCL exchanges); "
+                            "hetrd trailing matrix 1-D block-cyclic with in-kernel NVLink exchange; potrf/stedc replicated "
+                            "(bitwise deterministic)" % args.gpus)
             if args.gpus > 1 else "single"}
 
 
@@ -342,21 +343,23 @@ def main():
     torch.cuda.synchronize()
     A = torch.empty_like(a0)
     B = torch.empty_like(b0)
-    ws = api.Workspace(n, cplx, host_z=not args.no_e2e)
-    if not args.no_e2e:
-        a_host = torch.empty((n, n), dtype=dt, pin_memory=True)
-        b_host = torch.empty((n, n), dtype=dt, pin_memory=True)
-        a_host.copy_(a0)
-        b_host.copy_(b0)
-
+    ws = api.Workspace(n, cplx, host_z=(not args.no_e2e) and rank == 0)
+    c0, c1 = 0, n
     if world > 1:
         from eigensolver_gpu_b200 import multi_gpu as MG
-        mg_backend = MG.CudaStages()
+        MG.mg_init()                                   # library-owned NCCL communicator behind the C ABI
+        c0, c1 = MG.column_ranges(n, world)[rank]
+    if not args.no_e2e:
+        # pinned host images; with N ranks every rank holds (and uploads) only its 1/N column slice
+        a_host = torch.empty((c1 - c0, n), dtype=dt, pin_memory=True)
+        b_host = torch.empty((c1 - c0, n), dtype=dt, pin_memory=True)
+        a_host.copy_(a0[c0:c1])
+        b_host.copy_(b0[c0:c1])
     last = {}
 
     def solve_device(single=False):
         if world > 1 and not single:
-            info, w, z = MG.hegvdx_distributed(A, B, 1, m, backend=mg_backend, gather_z=True)
+            info, w, z, _ = api.solve_generalized_mg(A, B, 1, m, ws=ws, skip_host_copy=True)
         else:
             info, w, z, _ = api.solve_generalized(A, B, 1, m, ws=ws, skip_host_copy=True)
         if info != 0:
@@ -384,13 +387,13 @@ def main():
             if info != 0:
                 raise SystemExit("solve failed: " + lib.eigb200_last_error().decode())
             return
-        A.copy_(a_host, non_blocking=True)
-        B.copy_(b_host, non_blocking=True)
-        info, w, z = MG.hegvdx_distributed(A, B, 1, m, backend=mg_backend, gather_z=True)
-        if rank == 0:
-            ws.Z_h[:m].copy_(z)
-            ws.w_h.copy_(w)
-            torch.cuda.synchronize()
+        # every rank uploads its column slice over its own PCIe link, the slices are assembled over NVLink; the result
+        # (Z(:,1:m), w) is read back to the host of rank 0
+        A[c0:c1].copy_(a_host, non_blocking=True)
+        B[c0:c1].copy_(b_host, non_blocking=True)
+        MG.mg_allgather_columns(B)
+        MG.mg_allgather_columns(A)
+        info, w, z, _ = api.solve_generalized_mg(A, B, 1, m, ws=ws, skip_host_copy=(rank != 0))
         if info != 0:
             raise SystemExit("solve failed: " + lib.eigb200_last_error().decode())
 
@@ -478,6 +481,7 @@ def main():
 
     if rank != 0:
         if world > 1:
+            MG.mg_finalize()
             dist.destroy_process_group()
         return 0
 
@@ -550,6 +554,7 @@ def main():
                                           f"(--impl reference) times the real order once"}
     print(json.dumps(line), flush=True)
     if world > 1:
+        MG.mg_finalize()
         dist.destroy_process_group()
     return 0
 

@@ -24,6 +24,11 @@ SIGNATURES = {
     "eigb200_mg_alloc": (_i, [C.c_longlong, C.POINTER(C.c_void_p), C.c_char_p]),
     "eigb200_mg_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "eigb200_mg_config": (_i, [_i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_longlong, _p]),
+    "eigb200_mg_unique_id": (_i, [C.c_char_p]),
+    "eigb200_mg_init": (_i, [_i, _i, C.c_char_p]),
+    "eigb200_mg_finalize": (_i, []),
+    "eigb200_mg_allgather_columns": (_i, [_p, _i, _i, _i]),
+    "eigb200_mg_column_range": (_i, [_i, _i, _i, _ip, _ip]),
     "eigb200_prof_enable": (_i, [_i]),
     "eigb200_prof_reset": (_i, []),
     "eigb200_prof_collect": (_i, [_p, _p, _p]),
@@ -34,6 +39,9 @@ SIGNATURES = {
     "eigb200_dsygvdx": (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _ip, _i]),
     "eigb200_zhegvdx": (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i,
                              _p, _ip, _i]),
+    "eigb200_dsygvdx_mg": (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _ip, _i]),
+    "eigb200_zhegvdx_mg": (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i,
+                                _p, _ip, _i]),
     "eigb200_dsyevd": (_i, [_i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _ip]),
     "eigb200_zheevd": (_i, [_i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p, _ip]),
     "eigb200_dpotrf": (_i, [_i, _p, _i, _ip]),

@@ -57,6 +57,29 @@ def zhegvdx_gpu(N, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, rwork, lrwork
     return info.value
 
 
+def dsygvdx_gpu_mg(N, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, work_h, lwork_h, iwork_h, liwork_h, Z_h, ldz_h, w_h,
+                   _skip_host_copy=False):
+    """Multi-GPU entry (collective over the ranks of multi_gpu.mg_init): same argument list as dsygvdx_gpu."""
+    lib = load()
+    _sync_stream()
+    info = C.c_int(0)
+    lib.eigb200_dsygvdx_mg(N, _dp(A), lda, _dp(B), ldb, _dp(Z), ldz, il, iu, _dp(w), _dp(work), lwork, _dp(work_h), lwork_h,
+                           _dp(iwork_h), liwork_h, _dp(Z_h), ldz_h, _dp(w_h), C.byref(info), 1 if _skip_host_copy else 0)
+    return info.value
+
+
+def zhegvdx_gpu_mg(N, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, rwork, lrwork, work_h, lwork_h, rwork_h, lrwork_h,
+                   iwork_h, liwork_h, Z_h, ldz_h, w_h, _skip_host_copy=False):
+    """Multi-GPU entry (collective over the ranks of multi_gpu.mg_init): same argument list as zhegvdx_gpu."""
+    lib = load()
+    _sync_stream()
+    info = C.c_int(0)
+    lib.eigb200_zhegvdx_mg(N, _dp(A), lda, _dp(B), ldb, _dp(Z), ldz, il, iu, _dp(w), _dp(work), lwork, _dp(rwork), lrwork,
+                           _dp(work_h), lwork_h, _dp(rwork_h), lrwork_h, _dp(iwork_h), liwork_h, _dp(Z_h), ldz_h, _dp(w_h),
+                           C.byref(info), 1 if _skip_host_copy else 0)
+    return info.value
+
+
 def dsyevd_gpu(jobz, uplo, il, iu, N, A, lda, Z, ldz, w, work, lwork, work_h, lwork_h, iwork_h, liwork_h, Z_h, ldz_h, w_h):
     """dsyevd_gpu.F90:32-33 (jobz='V', uplo='U' only, as in the reference)."""
     if jobz != "V" or uplo != "U":
@@ -104,6 +127,21 @@ class Workspace:
         pin = pinned and torch.cuda.is_available()
         self.w_h = torch.empty(max(n, 1), dtype=torch.float64, pin_memory=pin)
         self.Z_h = torch.empty((n, n), dtype=dt, pin_memory=pin) if host_z else None
+
+
+def solve_generalized_mg(a_dev, b_dev, il, iu, ws=None, skip_host_copy=True):
+    """Collective multi-GPU solve through eigb200_{dsygvdx,zhegvdx}_mg (call multi_gpu.mg_init first): every rank passes the
+    same A, B; every rank gets (info, w[all n], Z view of the m eigenvector columns as (m, n) tensor, ws)."""
+    n = a_dev.shape[0]
+    cplx = a_dev.dtype == torch.complex128
+    ws = ws or Workspace(n, cplx, device=a_dev.device, host_z=not skip_host_copy)
+    if cplx:
+        info = zhegvdx_gpu_mg(n, a_dev, n, b_dev, n, ws.Z, n, il, iu, ws.w, ws.work, ws.lwork, ws.rwork, ws.lrwork, None,
+                              ws.lwork_h, None, ws.lrwork_h, None, ws.liwork_h, ws.Z_h, n, ws.w_h, skip_host_copy)
+    else:
+        info = dsygvdx_gpu_mg(n, a_dev, n, b_dev, n, ws.Z, n, il, iu, ws.w, ws.work, ws.lwork, None, ws.lwork_h, None,
+                              ws.liwork_h, ws.Z_h, n, ws.w_h, skip_host_copy)
+    return info, ws.w, ws.Z[: iu - il + 1], ws
 
 
 def solve_generalized(a_dev, b_dev, il, iu, ws=None, skip_host_copy=True, a_ready_event=None):

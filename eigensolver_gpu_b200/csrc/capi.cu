@@ -53,6 +53,25 @@ int eigb200_mg_config(int rank, int world, void** wbufs, void** flags, long long
   M.rank = rank; M.P = world; M.wbuf_bytes = wbuf_bytes;
   for (int q = 0; q < world; ++q) { M.wbuf[q] = wbufs ? wbufs[q] : nullptr; M.flags[q] = flags ? (unsigned long long*)flags[q] : nullptr; }
   M.hook = (panel_hook_t)panel_hook;
+  M.active = world > 1;
+  return 0;
+}
+int eigb200_mg_unique_id(char* id128) {
+  API_BEGIN();
+  return mg_unique_id(id128);
+}
+int eigb200_mg_init(int rank, int world, const char* id128) {
+  API_BEGIN();
+  return mg_init(rank, world, id128);
+}
+int eigb200_mg_finalize(void) { return mg_finalize(); }
+int eigb200_mg_allgather_columns(void* M_d, int ld, int ncols, int elem_bytes) {
+  API_BEGIN();
+  return mg_allgather_columns(ctx().stream, M_d, ld, ncols, elem_bytes);
+}
+int eigb200_mg_column_range(int ncols, int world, int rank, int* c0, int* c1) {
+  if (world < 1 || rank < 0 || rank >= world) return -1;
+  mg_column_range(ncols, world, rank, *c0, *c1);
   return 0;
 }
 
@@ -192,6 +211,27 @@ int eigb200_zhegvdx(int n, void* A, int lda, void* B, int ldb, void* Z, int ldz,
   return hegvdx_driver<double2>(n, (double2*)A, lda, (double2*)B, ldb, (double2*)Z, ldz, il, iu, w, (double2*)work,
                                 lwork, rwork, lrwork, lwork_h, lrwork_h, liwork_h, (double2*)Z_h, ldz_h, w_h, info,
                                 skip_host_copy);
+}
+int eigb200_dsygvdx_mg(int n, double* A, int lda, double* B, int ldb, double* Z, int ldz, int il, int iu, double* w,
+                       double* work, int lwork, double* work_h, int lwork_h, int* iwork_h, int liwork_h, double* Z_h,
+                       int ldz_h, double* w_h, int* info, int skip_host_copy) {
+  (void)work_h; (void)iwork_h;
+  int dummy = 0;
+  if (!info) info = &dummy;
+  if (ctx_init() != 0) { *info = -1; return -1; }
+  return hegvdx_mg_driver<double>(n, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, nullptr, 0, lwork_h, 0, liwork_h, Z_h,
+                                  ldz_h, w_h, info, skip_host_copy);
+}
+int eigb200_zhegvdx_mg(int n, void* A, int lda, void* B, int ldb, void* Z, int ldz, int il, int iu, double* w, void* work,
+                       int lwork, double* rwork, int lrwork, void* work_h, int lwork_h, double* rwork_h, int lrwork_h,
+                       int* iwork_h, int liwork_h, void* Z_h, int ldz_h, double* w_h, int* info, int skip_host_copy) {
+  (void)work_h; (void)rwork_h; (void)iwork_h;
+  int dummy = 0;
+  if (!info) info = &dummy;
+  if (ctx_init() != 0) { *info = -1; return -1; }
+  return hegvdx_mg_driver<double2>(n, (double2*)A, lda, (double2*)B, ldb, (double2*)Z, ldz, il, iu, w, (double2*)work,
+                                   lwork, rwork, lrwork, lwork_h, lrwork_h, liwork_h, (double2*)Z_h, ldz_h, w_h, info,
+                                   skip_host_copy);
 }
 int eigb200_dsyevd(int il, int iu, int n, double* A, int lda, double* Z, int ldz, double* w, double* work, int lwork,
                    double* work_h, int lwork_h, int* iwork_h, int liwork_h, double* Z_h, int ldz_h, double* w_h,

@@ -176,6 +176,8 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
   if (!strcmp(name, "trd_prefetch")) { if (value < -1 || value > 64) return -1; o.trd_prefetch = value; return 0; }
   if (!strcmp(name, "mg_switch_n")) { o.mg_switch_n = value; return 0; }
+  if (!strcmp(name, "mg_dist_min_n")) { o.mg_dist_min_n = value; return 0; }
+  if (!strcmp(name, "mg_gather_z")) { o.mg_gather_z = value; return 0; }
   if (!strcmp(name, "verbose")) { ctx().verbose = value; return 0; }
   return -1;
 }
@@ -192,6 +194,8 @@ int get_option(const char* name) {
   if (!strcmp(name, "trd_upc")) return o.trd_upc;
   if (!strcmp(name, "trd_prefetch")) return o.trd_prefetch;
   if (!strcmp(name, "mg_switch_n")) return o.mg_switch_n;
+  if (!strcmp(name, "mg_dist_min_n")) return o.mg_dist_min_n;
+  if (!strcmp(name, "mg_gather_z")) return o.mg_gather_z;
   if (!strcmp(name, "verbose")) return ctx().verbose;
   return -1;
 }

@@ -71,19 +71,14 @@ int copy_results_to_host(cudaStream_t s, int n, int m, const T* Z, int64_t ldz, 
     }                                                                                          \
   } while (0)
 
+// workspace / argument checks shared by the single- and multi-GPU drivers: zhegvdx_gpu.F90:106-127 /
+// dsygvdx_gpu.F90:100-113 (64-bit arithmetic: the reference's 1+5N+2N*N overflows default integers at N >= 32767)
 template <typename T>
-int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, int iu, double* w, T* work, int lwork,
-                  double* rwork, int lrwork, int lwork_h, int lrwork_h, int liwork_h, T* Z_h, int ldz_h, double* w_h,
-                  int* info, int skip_host_copy) {
+int hegvdx_check_args(int n, int lda, int ldb, int ldz, int il, int iu, int lwork, int lrwork, int lwork_h, int lrwork_h,
+                      int liwork_h, int* info) {
   const bool cplx = is_cplx<T>::value;
-  *info = 0;
   const char* name = cplx ? "zhegvdx_gpu" : "dsygvdx_gpu";
-  // the "A is ready" event is one-shot: consumed by this call whatever its outcome
-  cudaEvent_t a_ready = ctx().a_ready;
-  ctx().a_ready = nullptr;
   const int64_t N = n;
-  // workspace checks: zhegvdx_gpu.F90:106-127 / dsygvdx_gpu.F90:100-113 (64-bit arithmetic: the reference's
-  // 1+5N+2N*N overflows default integers at N >= 32767)
   const char* msg = nullptr;
   if (cplx) {
     if (lwork < 2 * 64 * 64 + 65 * N) msg = "lwork must be at least 2*64*64 + 65*N";
@@ -108,6 +103,22 @@ int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, in
     *info = -1;
     return -1;
   }
+  return 0;
+}
+template int hegvdx_check_args<double>(int, int, int, int, int, int, int, int, int, int, int, int*);
+template int hegvdx_check_args<double2>(int, int, int, int, int, int, int, int, int, int, int, int*);
+
+template <typename T>
+int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, int iu, double* w, T* work, int lwork,
+                  double* rwork, int lrwork, int lwork_h, int lrwork_h, int liwork_h, T* Z_h, int ldz_h, double* w_h,
+                  int* info, int skip_host_copy) {
+  const bool cplx = is_cplx<T>::value;
+  *info = 0;
+  const char* name = cplx ? "zhegvdx_gpu" : "dsygvdx_gpu";
+  // the "A is ready" event is one-shot: consumed by this call whatever its outcome
+  cudaEvent_t a_ready = ctx().a_ready;
+  ctx().a_ready = nullptr;
+  if (hegvdx_check_args<T>(n, lda, ldb, ldz, il, iu, lwork, lrwork, lwork_h, lrwork_h, liwork_h, info) != 0) return -1;
   if (n == 0) return 0;
   cudaStream_t s = ctx().stream;
   const int m = iu - il + 1;

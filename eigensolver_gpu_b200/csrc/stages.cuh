@@ -16,6 +16,8 @@ struct Options {
   int symv_tma = 1;     // stage symv/hemv tiles through TMA (cp.async.bulk.tensor) when alignment allows
   int trd_coop = 1;     // persistent cooperative panel kernel (0: one launch per phase)
   int mg_switch_n = 3072; // multi-GPU hetrd: below this trailing order all ranks continue replicated
+  int mg_dist_min_n = -1; // multi-GPU driver: distribute the tridiagonalization from this order on (-1: 6144 for 2 ranks, else 4096)
+  int mg_gather_z = 1;    // multi-GPU driver: gather the eigenvector column blocks so that every rank holds Z(:, 1:m)
   int trd_upc = 3;      // tile engine: target number of tile units per CTA (strip length heuristic)
   int trd_prefetch = 0; // tiles per CTA prefetched into L2 during phase A (-1: 256 KB worth, 0: off -- no gain measured)
   int hegst_hb = 0;     // block size of the reduction to standard form (0: 2048 for n >= 4096, else 1024)
@@ -34,9 +36,20 @@ struct MgConfig {
   unsigned long long* flags[8] = {nullptr};
   int64_t wbuf_bytes = 0;                 // size of ONE rank's exchange buffer
   unsigned long long seq = 0;             // monotonic column sequence number (flags never reset)
-  panel_hook_t hook = nullptr;            // called before every panel: broadcast of the panel's columns from `owner`
+  panel_hook_t hook = nullptr;            // legacy (caller-owned communicator): called before every panel to broadcast its columns
+  void* comm = nullptr;                   // ncclComm_t created by eigb200_mg_init (library-owned communicator)
+  bool own_exchange = false;              // exchange buffers allocated/mapped by mg_ensure_exchange (not handed in by mg_config)
+  bool active = false;                    // distribute the NEXT tridiagonalization (set by the multi-GPU driver / mg_config)
 };
 MgConfig& mg();
+// multi-GPU plumbing (mg.cu)
+void mg_column_range(int ncols, int world, int rank, int& c0, int& c1);
+int mg_unique_id(char* id128);
+int mg_init(int rank, int world, const char* id128);
+int mg_finalize();
+int mg_ensure_exchange(cudaStream_t s, int n);
+int mg_bcast_columns(cudaStream_t s, void* A, int64_t ld, int c0, int nc, int owner, int elem_bytes);
+int mg_allgather_columns(cudaStream_t s, void* A, int64_t ld, int ncols, int elem_bytes);
 }
 #include <vector>
 namespace eigb200 {
@@ -78,6 +91,13 @@ template <typename T>
 int hegvdx_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, int iu, double* w, T* work, int lwork,
                   double* rwork, int lrwork, int lwork_h, int lrwork_h, int liwork_h, T* Z_h, int ldz_h, double* w_h,
                   int* info, int skip_host_copy);
+template <typename T>
+int hegvdx_check_args(int n, int lda, int ldb, int ldz, int il, int iu, int lwork, int lrwork, int lwork_h, int lrwork_h,
+                      int liwork_h, int* info);
+template <typename T>
+int hegvdx_mg_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il, int iu, double* w, T* work, int lwork,
+                     double* rwork, int lrwork, int lwork_h, int lrwork_h, int liwork_h, T* Z_h, int ldz_h, double* w_h,
+                     int* info, int skip_host_copy);
 template <typename T>
 int heevd_driver(int il, int iu, int n, T* A, int lda, T* Z, int ldz, double* w, T* work, int lwork, double* rwork,
                  int lrwork, T* Z_h, int ldz_h, double* w_h, int* info);

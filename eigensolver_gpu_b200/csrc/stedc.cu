@@ -59,11 +59,16 @@ __global__ void dc_scale_kernel(DcWork w) {
   double mx = 0.0;
   bool bad = false;
   for (int i = threadIdx.x; i < w.n; i += blockDim.x) {
+    // NaN/Inf in T: every comparison-based step below (ranks, deflation, column maps) would go wrong in silence or index
+    // out of bounds.  Report through the status word and continue on a sanitised copy so that nothing can fault.
+    if (!isfinite(w.D[i])) { bad = true; w.D[i] = 0.0; }
     mx = fmax(mx, fabs(w.D[i]));
-    bad |= !isfinite(w.D[i]);
-    if (i < w.n - 1) { mx = fmax(mx, fabs(w.E[i])); bad |= !isfinite(w.E[i]); }
+    if (i < w.n - 1) {
+      if (!isfinite(w.E[i])) { bad = true; w.E[i] = 0.0; }
+      mx = fmax(mx, fabs(w.E[i]));
+    }
   }
-  if (bad) atomicMax(w.status, 3);            // NaN/Inf in T: comparisons below would silently drop it
+  if (bad) atomicMax(w.status, 3);
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();

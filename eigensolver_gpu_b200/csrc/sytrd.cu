@@ -1325,7 +1325,8 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   MgConfig& M = mg();
   p.rank = 0; p.P = 1;
   GemmParams<T>* GP = nullptr;
-  if (M.P > 1) {
+  const bool dist = M.P > 1 && M.active;
+  if (dist) {
     if (!opts().trd_coop) { set_last_error("hetrd: multi-GPU needs the cooperative panel kernel"); return -1; }
     if (nb != TB) { set_last_error("hetrd: multi-GPU needs trd_nb == 64 (panels aligned to the tile columns)"); return -1; }
     p.rank = M.rank; p.P = M.P;
@@ -1348,7 +1349,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   const bool coop = opts().trd_coop != 0;
   std::vector<GemmParams<T>> hp_all;          // multi-GPU: rank-2k parameter blocks, panel after panel
   std::vector<int> hp_off;
-  if (M.P > 1) {
+  if (dist) {
     int hi2 = n;
     while (hi2 > 0) {
       int nbp2 = hi2 < nb ? hi2 : nb;
@@ -1383,10 +1384,11 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     // the first (rightmost) panel absorbs the remainder so that the others are aligned to nb
     if (hi > nb && (hi % nb) != 0) nbp = hi % nb;
     p.i0 = hi - nbp; p.nbp = nbp;
-    if (M.P > 1 && p.P > 1 && hi <= opts().mg_switch_n) {
+    if (dist && p.P > 1 && hi <= opts().mg_switch_n) {
       // small trailing matrix: the per-column exchange costs more than the tiles it saves.  Make the leading hi
       // columns current everywhere (owner = -1: "gather all tile columns") and finish replicated (deterministic).
       if (M.hook) M.hook(hi, 0, -1);
+      else if (mg_bcast_columns(s, A, lda, hi, 0, -1, (int)sizeof(T)) != 0) return -1;
       p.P = 1; p.rank = 0;
     }
     if (p.P > 1) {
@@ -1394,6 +1396,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
       M.seq += (unsigned long long)nbp;
       // the panel's columns are current only on the rank that owns this tile column: broadcast them
       if (M.hook) M.hook(p.i0, nbp, (p.i0 / TB) % M.P);
+      else if (mg_bcast_columns(s, A, lda, p.i0, nbp, (p.i0 / TB) % M.P, (int)sizeof(T)) != 0) return -1;
     }
     prof_begin(PROF_PANEL, s);
     EIGB_CUDA_CHECK(cudaMemsetAsync(p.barrier, 0, (64 + NBMAX) * sizeof(unsigned), s));

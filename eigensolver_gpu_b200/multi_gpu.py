@@ -17,6 +17,37 @@ import torch
 import torch.distributed as dist
 
 
+def mg_init(group=None):
+    """Rendezvous of the library-owned NCCL communicator (eigb200_mg_unique_id / eigb200_mg_init): rank 0 creates the id,
+    torch.distributed carries the 128 bytes -- an MPI caller would MPI_Bcast them.  Afterwards api.solve_generalized_mg /
+    eigb200_{dsygvdx,zhegvdx}_mg are collective over these ranks."""
+    import ctypes as C
+    from ._lib import check, load
+    lib = load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        check(lib.eigb200_mg_unique_id(buf), "mg_unique_id")
+    box = [buf.raw]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    check(lib.eigb200_mg_init(rank, world, box[0]), "mg_init")
+    return rank, world
+
+
+def mg_finalize():
+    from ._lib import load
+    load().eigb200_mg_finalize()
+
+
+def mg_allgather_columns(t, ncols=None):
+    """t: (cols, ld) column-major device tensor whose contiguous column block column_ranges(...)[rank] is current on this
+    rank; afterwards all blocks are current everywhere (NCCL over NVLink, library-owned communicator)."""
+    from ._lib import check, sync_stream
+    lib = sync_stream()
+    ncols = t.shape[0] if ncols is None else ncols
+    check(lib.eigb200_mg_allgather_columns(t.data_ptr(), t.shape[1], ncols, t.element_size()), "mg_allgather_columns")
+
+
 def column_ranges(ncols, world, align=64):
     """Contiguous column ranges [c0, c1) per rank, boundaries aligned to `align` (the TRSM/tile block size)."""
     nblk = (ncols + align - 1) // align

@@ -47,6 +47,18 @@ int eigb200_get_option(const char* name);
 int eigb200_mg_alloc(long long bytes, void** dptr, char* handle64);
 int eigb200_mg_open(const char* handle64, void** dptr);
 int eigb200_mg_config(int rank, int world, void** wbufs, void** flags, long long wbuf_bytes, void* panel_hook);
+/* Library-owned communicator (what a Fortran/MPI caller uses; the functions above remain for callers that own the
+ * communicator themselves).  Rendezvous: rank 0 calls eigb200_mg_unique_id (ncclGetUniqueId), the caller distributes the
+ * 128 bytes (MPI_Bcast, torch.distributed, a file ...), then EVERY rank calls eigb200_mg_init with the device it will
+ * compute on current.  NCCL is resolved at run time (dlopen of libnccl.so.2); world <= 8 ranks on one NVLink domain.
+ * mg_allgather_columns: every rank owns the contiguous column block eigb200_mg_column_range(ncols, world, rank) (64-column
+ * aligned) of the ld x ncols device matrix; afterwards all ranks hold all blocks -- e.g. to upload 1/world of A per rank
+ * over PCIe and assemble over NVLink. */
+int eigb200_mg_unique_id(char* id128);
+int eigb200_mg_init(int rank, int world, const char* id128);
+int eigb200_mg_finalize(void);
+int eigb200_mg_allgather_columns(void* M_d, int ld, int ncols, int elem_bytes);
+int eigb200_mg_column_range(int ncols, int world, int rank, int* c0, int* c1);
 
 /* optional profiling: CUDA-event timing per stage category and a count of the kernels this library launched.
  * categories (index into ms[8], cnt[8]): 0 potrf, 1 hegst, 2 hetrd panel kernel, 3 hetrd rank-2k update,
@@ -76,6 +88,20 @@ int eigb200_zhegvdx(int n, void* A_d, int lda, void* B_d, int ldb, void* Z_d, in
                     double* w_d, void* work_d, int lwork, double* rwork_d, int lrwork, void* work_h,
                     int lwork_h, double* rwork_h, int lrwork_h, int* iwork_h, int liwork_h, void* Z_h,
                     int ldz_h, double* w_h, int* info, int skip_host_copy);
+
+/* ---- multi-GPU generalized drivers: ONE problem over the ranks of eigb200_mg_init (no reference analogue: the reference
+ * is single-GPU).  Same argument lists and checks as above; collective: every rank calls with the SAME A, B
+ * (replicated device inputs) and its own buffers.  On exit on every rank: B <- U, w(1:N), Z(:,1:m) (column blocks gathered
+ * unless option "mg_gather_z" = 0), host copies as requested; A is destroyed in BOTH triangles (Z serves as workspace).
+ * Partition: hegst / back-transform / final solve by right-hand-side columns, hetrd trailing matrix 1-D block-cyclic with the
+ * per-column exchange inside the panel kernel over NVLink, potrf and stedc replicated.  world == 1: the single-GPU driver. */
+int eigb200_dsygvdx_mg(int n, double* A_d, int lda, double* B_d, int ldb, double* Z_d, int ldz, int il, int iu,
+                       double* w_d, double* work_d, int lwork, double* work_h, int lwork_h, int* iwork_h,
+                       int liwork_h, double* Z_h, int ldz_h, double* w_h, int* info, int skip_host_copy);
+int eigb200_zhegvdx_mg(int n, void* A_d, int lda, void* B_d, int ldb, void* Z_d, int ldz, int il, int iu,
+                       double* w_d, void* work_d, int lwork, double* rwork_d, int lrwork, void* work_h,
+                       int lwork_h, double* rwork_h, int lrwork_h, int* iwork_h, int liwork_h, void* Z_h,
+                       int ldz_h, double* w_h, int* info, int skip_host_copy);
 
 /* ---- standard drivers: dsyevd_gpu.F90:32-33 / zheevd_gpu.F90:32-33 (jobz='V', uplo='U') ---------------- */
 int eigb200_dsyevd(int il, int iu, int n, double* A_d, int lda, double* Z_d, int ldz, double* w_d,

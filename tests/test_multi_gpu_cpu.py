@@ -106,3 +106,20 @@ def test_column_ranges_cover_and_align():
                 assert a1 == b0 and a0 <= a1
             for c0, c1 in r[:-1]:
                 assert c1 % 64 == 0 or c1 == n
+
+
+def test_c_side_column_partition_matches_the_python_one():
+    """eigb200_mg_column_range (mg.cu) is the partition the C-ABI multi-GPU driver uses; multi_gpu.column_ranges is the one
+    the gloo tests above exercise: they must be the same function"""
+    import ctypes as C
+    from eigensolver_gpu_b200 import multi_gpu as MG
+    from eigensolver_gpu_b200._lib import load
+    lib = load()
+    c0, c1 = C.c_int(), C.c_int()
+    for ncols in (1, 63, 64, 65, 700, 2500, 8192, 16384, 32768, 4096 + 17):
+        for world in (1, 2, 3, 4, 8):
+            ref = MG.column_ranges(ncols, world)
+            for r in range(world):
+                assert lib.eigb200_mg_column_range(ncols, world, r, C.byref(c0), C.byref(c1)) == 0
+                assert (c0.value, c1.value) == ref[r]
+            assert ref[0][0] == 0 and ref[-1][1] == ncols

@@ -111,3 +111,47 @@ def test_distributed_tridiagonalization(world, cplx, n):
         _, dl, el, _ = lapack.hetrd(a)
         assert np.abs(d - dl).max() <= 20 * n * metrics.EPS * an
         assert np.abs(e - el).max() <= 20 * n * metrics.EPS * an
+
+
+def _worker_cabi(rank, world, port, cplx, n, il, iu, out):
+    """the product path: eigb200_{dsygvdx,zhegvdx}_mg behind the C ABI, library-owned NCCL communicator"""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from eigensolver_gpu_b200 import api, multi_gpu as MG, stages as S
+    from eigensolver_gpu_b200._lib import load
+    lib = load()
+    MG.mg_init()
+    assert lib.eigb200_set_option(b"mg_dist_min_n", 0) == 0 and lib.eigb200_set_option(b"mg_switch_n", 256) == 0
+    a, b = matgen.family_c(n, cplx, seed=5)
+    ad, bd = S.to_dev(np.triu(a)), S.to_dev(np.triu(b))
+    info, w, z, ws = api.solve_generalized_mg(ad, bd, il, iu, skip_host_copy=False)
+    zs = [torch.zeros_like(z) for _ in range(world)]
+    dist.all_gather(zs, z.contiguous())
+    same = all(torch.equal(zs[0], x) for x in zs)                  # gathered column blocks: every rank holds the same Z
+    if rank == 0:
+        out.put((info, S.to_host(w).copy(), np.array(S.to_host(z)), same, ws.w_h.numpy().copy(),
+                 np.array(ws.Z_h.numpy().T[:, : iu - il + 1]), np.array(S.to_host(bd))))
+    dist.barrier()
+    MG.mg_finalize()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("cplx,n,il,iu", [(False, 700, 1, 300), (True, 700, 3, 300), (True, 2500, 1, 2500), (False, 3000, 1, 400)])
+def test_c_abi_multi_gpu_driver(world, cplx, n, il, iu):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    info, w, z, same, w_h, z_h, bout = _spawn(_worker_cabi, world, (cplx, n, il, iu))
+    a, b = matgen.family_c(n, cplx, seed=5)
+    wr, zr, ur, linfo = lapack.hegvd(a, b)
+    assert info == 0 and same
+    assert np.abs(w - wr).max() < n * metrics.EPS * np.linalg.norm(a, 2)
+    g = metrics.eig_gates(a, b, w[il - 1:iu], z)
+    assert g["residual_max"] < 30 and g["b_orth"] < 30
+    assert metrics.compare_2d_abs(zr[:, il - 1:iu], z)[0] < 1e-8
+    assert np.array_equal(w_h, w) and np.array_equal(z_h, z)
+    u = lapack.potrf(b)
+    assert np.abs(np.triu(bout) - u).max() <= 100 * n * metrics.EPS * np.abs(u).max()
