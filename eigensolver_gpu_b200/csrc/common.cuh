@@ -88,6 +88,7 @@ struct Context {
   cudaStream_t stream = 0;       // all hot-path work is issued here (default: legacy default stream,
                                  // like the reference's cuBLAS-legacy/default-stream ordering)
   cudaStream_t stream2 = nullptr;  // side stream for overlap (created lazily)
+  cudaStream_t stream_hi = nullptr;  // highest-priority side stream: latency-bound critical-path work next to a bulk update
   cudaEvent_t ev1 = nullptr, ev2 = nullptr;
   cudaEvent_t a_ready = nullptr;   // one-shot: the generalized driver waits for it before touching A
   void* scratch = nullptr;       // growable device scratch (stedc, panel partials, ...)

@@ -35,6 +35,8 @@ int ctx_init() {
     if (c.d_info) cudaFree(c.d_info);
     c.d_info = nullptr;
     if (c.stream2) cudaStreamDestroy(c.stream2);
+    if (c.stream_hi) cudaStreamDestroy(c.stream_hi);
+    c.stream_hi = nullptr;
     if (c.ev1) cudaEventDestroy(c.ev1);
     if (c.ev2) cudaEventDestroy(c.ev2);
     c.stream2 = nullptr; c.ev1 = c.ev2 = nullptr;
@@ -52,6 +54,11 @@ int ctx_init() {
   c.device = dev;
   c.num_sms = prop.multiProcessorCount;
   EIGB_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    EIGB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    EIGB_CUDA_CHECK(cudaStreamCreateWithPriority(&c.stream_hi, cudaStreamNonBlocking, hi));
+  }
   EIGB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev1, cudaEventDisableTiming));
   EIGB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev2, cudaEventDisableTiming));
   EIGB_CUDA_CHECK(cudaMalloc(&c.d_info, 64 * sizeof(int)));
@@ -173,6 +180,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "hegst_hb")) { if (value < 0) return -1; o.hegst_hb = value; return 0; }
   if (!strcmp(name, "trd_l2keep_mb")) { if (value < 0 || value > 4096) return -1; o.trd_l2keep_mb = value; return 0; }
   if (!strcmp(name, "trsm_leaf256")) { o.trsm_leaf256 = value; return 0; }
+  if (!strcmp(name, "potrf_pb")) { if (value > 8192) return -1; o.potrf_pb = value; return 0; }
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
   if (!strcmp(name, "trd_prefetch")) { if (value < -1 || value > 64) return -1; o.trd_prefetch = value; return 0; }
   if (!strcmp(name, "mg_switch_n")) { o.mg_switch_n = value; return 0; }
@@ -191,6 +199,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "hegst_hb")) return o.hegst_hb;
   if (!strcmp(name, "trd_l2keep_mb")) return o.trd_l2keep_mb;
   if (!strcmp(name, "trsm_leaf256")) return o.trsm_leaf256;
+  if (!strcmp(name, "potrf_pb")) return o.potrf_pb;
   if (!strcmp(name, "trd_upc")) return o.trd_upc;
   if (!strcmp(name, "trd_prefetch")) return o.trd_prefetch;
   if (!strcmp(name, "mg_switch_n")) return o.mg_switch_n;

@@ -452,6 +452,13 @@ int potrf_rec(cudaStream_t s, int lo, int hi, T* A, int64_t lda, T* Dinv, int* d
 }
 
 // Cholesky B = U^H U (upper, in place).  *info_h = 0 or the 1-based index of the first non-positive pivot.
+//
+// Right-looking by PB-wide block rows with ONE block of look-ahead on a high-priority side stream: the latency-bound
+// part of step k+1 (diagonal block: recursive, tiny grids; row panel: solves with 64x64 inverted blocks) runs next to the
+// bulk rank-PB update of step k, which fills the GPU on the caller's stream.  Below 2 PB the plain recursion is used.
+//   hi stream : potrf(D_k) -> U_k* = D_k^-H A_k* -> update of the NEXT block row  A_(k+1)* -= U_k,(k+1)^H U_k*
+//   main      : A_** -= U_k*^H U_k*  on the remaining trailing matrix (upper)
+// (the reference calls cusolverDn?potrf here, zhegvdx_gpu.F90:135)
 template <typename T>
 int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h, bool sync_status) {
   if (sync_status) *info_h = 0;
@@ -462,9 +469,62 @@ int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h, bool sync
   void* scr = ctx_scratch((size_t)nblk * NB * NB * sizeof(T) + 256);
   if (!scr) return -1;
   T* Dinv = (T*)scr;
-  int* dinfo = c.d_info + 1;
+  int* dinfo = c.d_info + ST_POTRF;
   EIGB_CUDA_CHECK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
-  if (potrf_rec<T>(s, 0, n, B, ldb, Dinv, dinfo) != 0) return -1;
+  const int PB = opts().potrf_pb > 0 ? ((opts().potrf_pb + NB - 1) / NB) * NB : 512;
+  if (n < 2 * PB || c.stream_hi == nullptr || opts().potrf_pb < 0) {
+    if (potrf_rec<T>(s, 0, n, B, ldb, Dinv, dinfo) != 0) return -1;
+  } else {
+    cudaStream_t sh = c.stream_hi;
+    TriInv<T> ti; ti.d64 = Dinv;
+    std::vector<cudaEvent_t> evs;
+    auto new_event = [&]() { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
+    int rc = 0;
+    cudaEvent_t e0 = new_event();
+    if (cudaEventRecord(e0, s) != cudaSuccess || cudaStreamWaitEvent(sh, e0, 0) != cudaSuccess) rc = -1;
+    cudaEvent_t ev_bulk_prev = nullptr;
+    for (int k0 = 0; k0 < n && rc == 0; k0 += PB) {
+      const int kb = n - k0 < PB ? n - k0 : PB;
+      const int r = n - k0 - kb;
+      // diagonal block and row panel on the high-priority stream (their inputs were updated by the look-ahead step)
+      if (potrf_rec<T>(sh, k0, k0 + kb, B, ldb, Dinv, dinfo) != 0) { rc = -1; break; }
+      if (r <= 0) break;
+      T* U12 = B + k0 + (int64_t)(k0 + kb) * ldb;                  // kb x r
+      if (trsm_rec<T>(sh, 'L', 'C', k0, k0 + kb, r, B, ldb, B + (int64_t)(k0 + kb) * ldb, ldb, ti) != 0) { rc = -1; break; }
+      cudaEvent_t ev_panel = new_event();
+      if (cudaEventRecord(ev_panel, sh) != cudaSuccess) { rc = -1; break; }
+      const int nb2 = r < PB ? r : PB;
+      T* A22 = B + (k0 + kb) + (int64_t)(k0 + kb) * ldb;           // r x r trailing matrix (upper)
+      // look-ahead: the next block row  A22(0:nb2, 0:r) -= U12(:, 0:nb2)^H U12(:, 0:r)  (upper part of its diagonal block).
+      // Rows of the next block were last written by the bulk update of the previous step: wait for it.
+      if (ev_bulk_prev && cudaStreamWaitEvent(sh, ev_bulk_prev, 0) != cudaSuccess) { rc = -1; break; }
+      {
+        GemmParams<T> p{};
+        p.M = nb2; p.N = r; p.nseg = 1;
+        p.A[0] = U12; p.lda[0] = ldb; p.B[0] = U12; p.ldb[0] = ldb; p.K[0] = kb;
+        p.A[1] = U12; p.lda[1] = ldb; p.B[1] = U12; p.ldb[1] = ldb; p.K[1] = 0;
+        p.sa[0] = p.sa[1] = -1.0; p.sb[0] = p.sb[1] = 1.0;
+        p.C = A22; p.ldc = ldb; p.alpha = -1.0; p.beta = 1.0; p.mode = 1; p.real_diag = 1; p.colmap = nullptr; p.diag_off = 0;
+        if (gemm_launch<T>(sh, true, true, p) != 0) { rc = -1; break; }
+      }
+      // bulk: the rest of the trailing matrix on the caller's stream, overlapping with the next diagonal block / panel
+      if (r > nb2) {
+        if (cudaStreamWaitEvent(s, ev_panel, 0) != cudaSuccess) { rc = -1; break; }
+        if (herk_upper<T>(s, 'C', r - nb2, kb, -1.0, U12 + (int64_t)nb2 * ldb, ldb, 1.0, A22 + nb2 + (int64_t)nb2 * ldb, ldb) != 0) {
+          rc = -1; break;
+        }
+        ev_bulk_prev = new_event();
+        if (cudaEventRecord(ev_bulk_prev, s) != cudaSuccess) { rc = -1; break; }
+      } else {
+        ev_bulk_prev = nullptr;
+      }
+    }
+    // join: everything issued on the side stream is ordered before what the caller's stream does next
+    cudaEvent_t ej = new_event();
+    if (cudaEventRecord(ej, sh) != cudaSuccess || cudaStreamWaitEvent(s, ej, 0) != cudaSuccess) rc = -1;
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (rc != 0) { if (cudaGetLastError() != cudaSuccess) set_last_error("potrf: stream/event call failed"); return -1; }
+  }
   if (sync_status) {
     EIGB_CUDA_CHECK(cudaMemcpyAsync(info_h, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
     EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
