@@ -57,6 +57,7 @@ SIGNATURES = {
     "eigb200_dgemm": (_i, [_c, _c, _i, _i, _i, _d, _p, _i, _p, _i, _d, _p, _i]),
     "eigb200_zgemm": (_i, [_c, _c, _i, _i, _i, _d, _p, _i, _p, _i, _d, _p, _i]),
     "eigb200_dstedc": (_i, [_i, _p, _p, _p, _i]),
+    "eigb200_dstedc_range": (_i, [_i, _p, _p, _p, _i, _i, _i]),
     "eigb200_dormtr": (_i, [_i, _i, _p, _i, _p, _p, _i]),
     "eigb200_zunmtr": (_i, [_i, _i, _p, _i, _p, _p, _i]),
     "eigb200_dtrsm": (_i, [_c, _c, _i, _i, _p, _i, _p, _i]),

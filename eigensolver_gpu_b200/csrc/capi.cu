@@ -145,6 +145,15 @@ int eigb200_dstedc(int n, double* d, double* e, double* Q, int ldq) {
   return 0;
 }
 
+int eigb200_dstedc_range(int n, double* d, double* e, double* Q, int ldq, int c_lo, int c_hi) {
+  API_BEGIN();
+  void* scr = ctx_scratch(stedc_scratch_bytes(n));
+  if (!scr) return -1;
+  if (stedc_device(ctx().stream, n, d, e, Q, ldq, scr, ctx().scratch_bytes, c_lo, c_hi) != 0) return -1;
+  if (status_fetch(ctx().stream) != 0) return -1;
+  if (ctx().h_status[ST_STEDC] != 0) { set_last_error("dstedc: device status %d (1 QL, 2 secular, 3 non-finite)", ctx().h_status[ST_STEDC]); return -1; }
+  return 0;
+}
 int eigb200_dpotrf(int n, double* B, int ldb, int* info_h) {
   API_BEGIN();
   return potrf_upper<double>(ctx().stream, n, B, ldb, info_h);

@@ -41,7 +41,8 @@ int heevd_core(cudaStream_t s, int n, int il, int iu, T* A, int64_t lda, T* Z, i
   char* scr = (char*)ctx_scratch(need);
   if (!scr) return -1;
   double* Qt = (double*)scr;
-  if (stedc_device(s, n, w, d_e, Qt, n, scr + ((nn + 255) & ~size_t(255)), ctx().scratch_bytes - ((nn + 255) & ~size_t(255))) != 0)
+  if (stedc_device(s, n, w, d_e, Qt, n, scr + ((nn + 255) & ~size_t(255)), ctx().scratch_bytes - ((nn + 255) & ~size_t(255)),
+                   il - 1, iu) != 0)
     return -1;
   select_columns_kernel<T><<<dim3(cdiv(n, 256), m), 256, 0, s>>>(Qt, n, n, il - 1, m, Z, ldz);
   EIGB_LAUNCH_CHECK();

@@ -308,7 +308,8 @@ int hegvdx_mg_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il,
   EIGB_MG_FAIL(scr == nullptr, "scratch allocation");
   double* Qt = (double*)scr;
   const size_t qoff = (nn + 255) & ~size_t(255);
-  EIGB_MG_FAIL(stedc_device(s, n, w, d_e, Qt, n, scr + qoff, ctx().scratch_bytes - qoff) != 0, "stedc");
+  // (eigenvectors of T only for this rank's columns: the root merge of the divide & conquer is thereby split over the ranks)
+  EIGB_MG_FAIL(stedc_device(s, n, w, d_e, Qt, n, scr + qoff, ctx().scratch_bytes - qoff, il - 1 + z0, il - 1 + z1) != 0, "stedc");
   if (mz > 0) {
     T* Zb = Z + (int64_t)z0 * ldz;
     select_columns_mg_kernel<T><<<dim3(cdiv(n, 256), mz), 256, 0, s>>>(Qt, n, n, il - 1 + z0, mz, Zb, ldz);

@@ -71,7 +71,7 @@ int status_check(const char* who, int* potrf_pivot = nullptr);
 // tridiagonal divide & conquer on the device
 size_t stedc_scratch_bytes(int n);
 int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t ldq, void* scratch,
-                 size_t scratch_bytes);
+                 size_t scratch_bytes, int c_lo = 0, int c_hi = 2147483647);
 
 // Cholesky / triangular solves / reduction to standard form (trsm.cu)
 template <typename T> int symmetrize_from_upper(cudaStream_t s, int n, T* A, int64_t lda, T* save, int64_t lds);

@@ -39,6 +39,7 @@ struct DcWork {
   int *idx, *typ, *srccol, *posg, *cmap, *dstcol, *rotp, *rotn, *permnd, *permdf;
   int *K;               // per merge: k, k1, k2, k3, nrot  (5 ints per merge)
   GemmParams<double>* gp;
+  int* sel;             // root merge restricted to the wanted columns: [j_lo, j_hi) of the non-deflated roots
   int* status;          // device status word: 1 leaf QL did not converge, 2 secular equation, 3 non-finite eigenvalue
 };
 
@@ -420,13 +421,14 @@ __global__ void __launch_bounds__(256) dc_zhat_kernel(DcWork w, int level) {
   if (lane == 0) w.zhat[g.lo + gi] = copysign(sqrt(fabs(p)), w.wz[g.lo + i]);
 }
 
-__global__ void __launch_bounds__(256) dc_formu_kernel(DcWork w, int level) {
+__global__ void __launch_bounds__(256) dc_formu_kernel(DcWork w, int level, int restricted) {
   const int m = blockIdx.y;
   const MergeGeom g = merge_geom(w, level, m);
   const int k = w.K[5 * m];
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= k) return;
+  if (restricted && (j < w.sel[0] || j >= w.sel[1])) return;     // column not wanted (root merge only)
   double* Xc = w.X + g.lo + (int64_t)(g.lo + j) * w.ldx;
   const double* zh = w.zhat + g.lo;
   if (k == 1) { if (lane == 0) Xc[0] = 1.0; return; }
@@ -437,16 +439,39 @@ __global__ void __launch_bounds__(256) dc_formu_kernel(DcWork w, int level) {
   for (int q = lane; q < k; q += 32) Xc[q] = (zh[q] / Xc[q]) * inv;
 }
 
-__global__ void dc_scatter_kernel(DcWork w, int level) {
+__global__ void dc_scatter_kernel(DcWork w, int level, int c_lo, int c_hi) {
   const int m = blockIdx.y;
   const MergeGeom g = merge_geom(w, level, m);
   const int k = w.K[5 * m];
   const int e = blockIdx.x;
   if (e >= g.n - k) return;
   const int dst = w.dstcol[g.lo + e];
+  if (dst < c_lo || dst >= c_hi) return;                         // (root merge with a restricted column range)
   const double* s = w.WS + g.lo + (int64_t)(g.lo + k + e) * w.ldw;
   double* d = w.Q + g.lo + (int64_t)(g.lo + dst) * w.ldq;
   for (int r = threadIdx.x; r < g.n; r += blockDim.x) d[r] = s[r];
+}
+
+// Root merge, eigenvectors wanted only for the final (sorted) columns [c_lo, c_hi): the roots are ascending, so their
+// final positions cmap[0..k) are increasing and the wanted ones form one contiguous range [j_lo, j_hi) of the
+// non-deflated columns.  Restrict the two GEMMs of the merge (their parameter blocks live in device memory) to it.
+__global__ void dc_restrict_kernel(DcWork w, int c_lo, int c_hi) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int k = w.K[0];
+  const int* cmap = w.cmap;           // root merge: lo = 0
+  int a = 0, b = k;
+  while (a < b) { const int mid = (a + b) >> 1; if (cmap[mid] < c_lo) a = mid + 1; else b = mid; }
+  const int j_lo = a;
+  b = k;
+  while (a < b) { const int mid = (a + b) >> 1; if (cmap[mid] < c_hi) a = mid + 1; else b = mid; }
+  const int j_hi = a;
+  w.sel[0] = j_lo; w.sel[1] = j_hi;
+  for (int half = 0; half < 2; ++half) {
+    GemmParams<double>& p = w.gp[half];
+    p.N = j_hi - j_lo;
+    p.B[0] += (int64_t)j_lo * w.ldx; p.B[1] = p.B[0];
+    p.colmap += j_lo;
+  }
 }
 
 __global__ void dc_identity_kernel(double* Q, int64_t ldq, int n) {
@@ -458,14 +483,20 @@ __global__ void dc_identity_kernel(double* Q, int64_t ldq, int n) {
 
 size_t stedc_scratch_bytes(int n) {
   size_t nn = (size_t)n * n;
-  return 2 * nn * sizeof(double) + (size_t)n * (10 * sizeof(double) + 10 * sizeof(int)) +
+  return 2 * nn * sizeof(double) + (size_t)n * (10 * sizeof(double) + 10 * sizeof(int)) + 4096 +
          (size_t)(n / 2 + 2) * (5 * sizeof(int) + 2 * sizeof(GemmParams<double>)) + 64 * 256;
 }
 
 // All eigenpairs of the symmetric tridiagonal (d, e): d <- eigenvalues ascending, Q <- eigenvectors.
 // e is destroyed.  `scratch` must provide stedc_scratch_bytes(n).
+// c_lo, c_hi (0-based, half open; 0, n = all): the eigenVECTOR columns the caller will read.  All n eigenvalues are always
+// computed; columns of Q outside the range are undefined on exit (the root merge skips them: with m << n requested
+// eigenpairs -- or a rank's share of them in the multi-GPU drivers -- the dominant GEMM shrinks by n / (c_hi - c_lo)).
 int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t ldq, void* scratch,
-                 size_t scratch_bytes) {
+                 size_t scratch_bytes, int c_lo, int c_hi) {
+  if (c_lo < 0) c_lo = 0;
+  if (c_hi > n) c_hi = n;
+  if (c_hi < c_lo) c_hi = c_lo;
   if (n <= 0) return 0;
   EIGB_CUDA_CHECK(cudaMemsetAsync(ctx().d_info + ST_STEDC, 0, sizeof(int), s));
   EIGB_CUDA_CHECK(cudaMemset2DAsync(Q, ldq * sizeof(double), 0, (size_t)n * sizeof(double), n, s));
@@ -492,6 +523,7 @@ int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t
   w.cmap = ar.take<int>(n); w.dstcol = ar.take<int>(n); w.rotp = ar.take<int>(n); w.rotn = ar.take<int>(n);
   w.permnd = ar.take<int>(n); w.permdf = ar.take<int>(n);
   w.K = ar.take<int>(5 * (size_t)(n / 2 + 2));
+  w.sel = ar.take<int>(8);
   w.gp = ar.take<GemmParams<double>>(2 * (size_t)(n / 2 + 2));
   if (!w.gp) { set_last_error("stedc: scratch arena exhausted"); return -1; }
   w.status = ctx().d_info + ST_STEDC;
@@ -519,13 +551,15 @@ int stedc_device(cudaStream_t s, int n, double* d, double* e, double* Q, int64_t
     dc_gather_kernel<<<gcol, 256, 0, s>>>(w, level);
     dc_secular_kernel<<<gwarp, 256, 0, s>>>(w, level);
     dc_rank_kernel<<<gthr, 256, 0, s>>>(w, level);
+    const bool restricted = level == levels && (c_lo > 0 || c_hi < n);
+    if (restricted) { dc_restrict_kernel<<<1, 32, 0, s>>>(w, c_lo, c_hi); count_launch(1); }
     dc_zhat_kernel<<<gwarp, 256, 0, s>>>(w, level);
-    dc_formu_kernel<<<gwarp, 256, 0, s>>>(w, level);
+    dc_formu_kernel<<<gwarp, 256, 0, s>>>(w, level, restricted ? 1 : 0);
     count_launch(7);
     EIGB_LAUNCH_CHECK();
     GemmParams<double> dummy{};
     if (gemm_launch<double>(s, false, true, dummy, w.gp, 2 * nmerge, maxn, maxn) != 0) return -1;
-    dc_scatter_kernel<<<gcol, 256, 0, s>>>(w, level);
+    dc_scatter_kernel<<<gcol, 256, 0, s>>>(w, level, restricted ? c_lo : 0, restricted ? c_hi : n);
     EIGB_LAUNCH_CHECK();
   }
   dc_unscale_kernel<<<cdiv(n, 256), 256, 0, s>>>(w);

@@ -85,15 +85,19 @@ def hetrd(a):
     return d, e[: n - 1], tau[: n - 1]
 
 
-def stedc(d, e):
-    """All eigenpairs of the tridiagonal (d, e) on the device. Returns (w, Q) with Q as (n, n) column-major tensor."""
+def stedc(d, e, cols=None):
+    """All eigenvalues of the tridiagonal (d, e) on the device and the eigenvectors (all, or only the sorted columns
+    cols = (c_lo, c_hi), 0-based half open -- the others are undefined). Returns (w, Q), Q an (n, n) column-major tensor."""
     lib = load()
     n = d.shape[0]
     w = d.clone()
     ee = torch.zeros(max(n, 1), dtype=torch.float64, device=d.device)
     ee[: n - 1] = e[: n - 1]
     q = torch.zeros((n, n), dtype=torch.float64, device=d.device)
-    check(lib.eigb200_dstedc(n, _ptr(w), _ptr(ee), _ptr(q), n), "stedc")
+    if cols is None:
+        check(lib.eigb200_dstedc(n, _ptr(w), _ptr(ee), _ptr(q), n), "stedc")
+    else:
+        check(lib.eigb200_dstedc_range(n, _ptr(w), _ptr(ee), _ptr(q), n, cols[0], cols[1]), "stedc")
     return w, q
 
 

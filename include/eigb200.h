@@ -138,6 +138,10 @@ int eigb200_zgemm(char transa, char transb, int m, int n, int k, double alpha, c
 /* all eigenpairs of the symmetric tridiagonal (d,e) on the device (replaces host ?stedc('I'),
  * dsyevd_gpu.F90:99 / zheevd_gpu.F90:101): w ascending in d_d, Q (n x n, real) in Q_d */
 int eigb200_dstedc(int n, double* d_d, double* e_d, double* Q_d, int ldq);
+/* same, eigenVECTORS only for the sorted columns [c_lo, c_hi) (0-based, half open; all n eigenvalues are still returned):
+ * the root merge of the divide & conquer skips the other columns, which are undefined on exit -- what the drivers use for
+ * il..iu subsets and what splits the merge over the ranks in the multi-GPU drivers */
+int eigb200_dstedc_range(int n, double* d_d, double* e_d, double* Q_d, int ldq, int c_lo, int c_hi);
 /* Z <- Q Z with Q from ?sytrd/?hetrd (back-transformation, dsyevd_gpu.F90:117-128 / zheevd_gpu.F90:119-130) */
 int eigb200_dormtr(int n, int m, const double* A_d, int lda, const double* tau_d, double* Z_d, int ldz);
 int eigb200_zunmtr(int n, int m, const void* A_d, int lda, const void* tau_d, void* Z_d, int ldz);

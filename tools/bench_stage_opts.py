@@ -1,4 +1,4 @@
-"""A/B timing of one stage under option settings: python tools/bench_stage_opts.py potrf|hegst|trsm N d|z name=value ..."""
+"""A/B timing of one stage under option settings: python tools/bench_stage_opts.py potrf|hegst|trsm|ormtr|stedc N d|z name=value ..."""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -27,6 +27,15 @@ for setting in sys.argv[4:]:
             S.potrf(B); e0.record(); S.hegst(A, B); e1.record()
         elif stage == "trsm":
             S.potrf(B); e0.record(); S.trsm("L", "N", B, A, m=n, n=n); e1.record()
+        elif stage == "ormtr":
+            d, e, tau = S.hetrd(A) if rep == 0 else (None, None, tau)
+            if rep == 0:
+                Ared = A.clone()
+            z = torch.eye(n, dtype=dt, device="cuda")
+            e0.record(); S.ormtr(Ared, tau, z, m=n); e1.record()
+        elif stage == "stedc":
+            dd = torch.randn(n, dtype=torch.float64, device="cuda"); ee = torch.randn(n - 1, dtype=torch.float64, device="cuda")
+            e0.record(); S.stedc(dd, ee); e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     print(f"{stage} {'z' if cplx else 'd'} n={n} [{setting}]: {best:.2f} ms", flush=True)
