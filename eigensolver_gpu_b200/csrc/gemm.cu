@@ -37,6 +37,28 @@ __device__ __forceinline__ void cp_async(void* smem, const void* gmem, int src_b
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(s), "l"(gmem), "r"(src_bytes));
   }
 }
+// ---- mbarrier-tracked cp.async ring (no CTA-wide barrier per k-tile) -------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_addr(bar)) : "memory");
+}
+// this thread's outstanding cp.async operations arrive on the barrier when they complete (count pre-accounted: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" :: "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned spins = 0;
+  while (!mbar_test(bar, parity)) { if (++spins > (1u << 26)) __trap(); }      // watchdog: fail, never hang
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
@@ -88,6 +110,10 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32, 2) gemm_kernel
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
+  // ring barriers: full[s] completes when every thread's cp.async writes into stage s have landed, empty[s] when all
+  // warps have read it.  The warps of a CTA are never aligned by a CTA-wide barrier inside the k loop: a warp that is
+  // ahead computes its next k-tile instead of waiting, which keeps the tensor pipe fed across k-tile boundaries.
+  __shared__ __align__(8) uint64_t ring_full[4], ring_empty[4];
 
   GemmParams<T> p = dev ? dev[blockIdx.z] : pv;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -95,6 +121,12 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32, 2) gemm_kernel
   if (p.mode == 1 && m0 > n0 + BN - 1 + p.diag_off) return;   // tile strictly below the diagonal
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < STAGES; ++st) { mbar_init(&ring_full[st], NT); mbar_init(&ring_empty[st], NT / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
   const int wm0 = (warp % WGM) * WTM, wn0 = (warp / WGM) * WTN;
   const int g = lane >> 2, t = lane & 3;
 
@@ -110,8 +142,18 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32, 2) gemm_kernel
       T* Bs = As + A_ELEMS;
       load_tile<T, AK, BM, PAD, CH, NT, BKT>(As, p.A[seg], p.lda[seg], m0, k0, p.M, p.K[seg], tid);
       load_tile<T, BK, BN, PAD, CH, NT, BKT>(Bs, p.B[seg], p.ldb[seg], n0, k0, p.N, p.K[seg], tid);
+      cp_async_mbar_arrive(&ring_full[kt % STAGES]);
     }
-    cp_async_commit();
+  };
+  // loads of k-tile j (j >= STAGES) reuse the stage of k-tile j - STAGES: all warps must have released it
+  auto stage_free = [&](int j, bool block) -> bool {
+    if (j >= KT) return true;                       // nothing to load
+    uint64_t* bar = &ring_empty[j % STAGES];
+    const unsigned par = (unsigned)((j / STAGES) - 1) & 1u;
+    if (block) { mbar_wait(bar, par); return true; }
+    unsigned ok = 0;
+    if (lane == 0) ok = mbar_test(bar, par) ? 1u : 0u;
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
   };
 
   double acc[MI][NI][CPLX ? 4 : 2];
@@ -136,9 +178,11 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32, 2) gemm_kernel
   }
 
   for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    issue(kt + STAGES - 1);
+    // refill the stage released one k-tile ago now if every warp is through with it, else after this k-tile's math
+    const int jn = kt + STAGES - 1;
+    const bool early = jn < STAGES || stage_free(jn, false);
+    if (early) issue(jn);
+    mbar_wait(&ring_full[kt % STAGES], (unsigned)(kt / STAGES) & 1u);
     const T* As = smem + (kt % STAGES) * (A_ELEMS + B_ELEMS);
     const T* Bs = As + A_ELEMS;
     double sa = 1.0, sb = 1.0;
@@ -187,8 +231,10 @@ __global__ void __launch_bounds__(Cfg<T>::WGM * Cfg<T>::WGN * 32, 2) gemm_kernel
           }
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring_empty[kt % STAGES]);
+    if (!early) { stage_free(jn, true); issue(jn); }
   }
-  cp_async_wait<0>();
 
   // epilogue: C = alpha*acc + beta*C.  All loads of a row group are issued before the first store: a store
   // followed by a load of another C element cannot be reordered by the compiler, and one DRAM round trip per
