@@ -181,6 +181,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "trd_l2keep_mb")) { if (value < 0 || value > 4096) return -1; o.trd_l2keep_mb = value; return 0; }
   if (!strcmp(name, "trsm_leaf256")) { o.trsm_leaf256 = value; return 0; }
   if (!strcmp(name, "potrf_pb")) { if (value > 8192) return -1; o.potrf_pb = value; return 0; }
+  if (!strcmp(name, "gemm_tma")) { o.gemm_tma = value; return 0; }
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
   if (!strcmp(name, "trd_prefetch")) { if (value < -1 || value > 64) return -1; o.trd_prefetch = value; return 0; }
   if (!strcmp(name, "mg_switch_n")) { o.mg_switch_n = value; return 0; }
@@ -200,6 +201,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "trd_l2keep_mb")) return o.trd_l2keep_mb;
   if (!strcmp(name, "trsm_leaf256")) return o.trsm_leaf256;
   if (!strcmp(name, "potrf_pb")) return o.potrf_pb;
+  if (!strcmp(name, "gemm_tma")) return o.gemm_tma;
   if (!strcmp(name, "trd_upc")) return o.trd_upc;
   if (!strcmp(name, "trd_prefetch")) return o.trd_prefetch;
   if (!strcmp(name, "mg_switch_n")) return o.mg_switch_n;

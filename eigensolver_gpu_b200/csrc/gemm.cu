@@ -316,6 +316,9 @@ int gemm_launch(cudaStream_t s, bool AK, bool BK, const GemmParams<T>& p, const 
                 int maxM, int maxN) {
   if (!dev) {
     if (p.M <= 0 || p.N <= 0) return 0;
+    // host-side parameters: the TMA-fed kernel (gemm_tma.cu) unless alignment forbids tensor maps or the option is off
+    const int r = gemm_launch_tma<T>(s, AK, BK, p);
+    if (r <= 0) return r;
   }
   // device-side parameter blocks cannot be inspected here: they must be 16-byte aligned by construction for
   // complex; for real the 8-byte chunk path is used unless the caller-side template says otherwise.

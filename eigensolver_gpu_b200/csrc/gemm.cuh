@@ -35,6 +35,10 @@ template <typename T>
 int gemm_launch(cudaStream_t s, bool AK, bool BK, const GemmParams<T>& p, const GemmParams<T>* dev_params = nullptr,
                 int batch = 1, int maxM = 0, int maxN = 0);
 
+// TMA-fed variant for host-side parameters (gemm_tma.cu): 0 launched, 1 not applicable (use the cp.async kernel), -1 error
+template <typename T>
+int gemm_launch_tma(cudaStream_t s, bool AK, bool BK, const GemmParams<T>& p);
+
 // CTA tile of the kernel for element type T (callers that need to know how many CTAs a shape produces)
 template <typename T> void gemm_tile_dims(int& bm, int& bn);
 

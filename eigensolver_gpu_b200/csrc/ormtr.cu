@@ -84,14 +84,24 @@ __global__ void bt_sum_slices_kernel(const T* __restrict__ Xs, int S, int64_t sl
   X[o] = acc;
 }
 
-// V^H Z has only ib rows: with few eigenvector columns it does not produce enough CTAs to fill the GPU, so its
-// K range (the block height) is split over up to 16 CTA groups whose partial products are summed afterwards.
-int bt_splits(int m, int ib, int esize) {
+// V^H Z has only ib rows: its tiles seldom fill the 2 x 148 CTA slots of the GPU evenly (m = 8192, ib = 128: 256 tiles on
+// 296 slots = one wave at 86 %; few eigenvector columns: a fraction of a wave).  Its K range (the block height) is
+// therefore split over S CTA groups whose partial products are summed afterwards; S minimises the number of waves per
+// unit of work, ceil(ntile S / slots) / S, with a small penalty per slice for the extra pass over the partial products.
+int bt_splits(int m, int ib, int esize, int cap = 16) {
   int bm, bn;
   if (esize == 16) gemm_tile_dims<double2>(bm, bn); else gemm_tile_dims<double>(bm, bn);
   const int ntile = ((ib + bm - 1) / bm) * ((m + bn - 1) / bn);
-  int S = 296 / (ntile > 0 ? ntile : 1);
-  return S < 1 ? 1 : (S > 16 ? 16 : S);
+  if (ntile <= 0) return 1;
+  const int slots = 2 * ctx().num_sms;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int S = 1; S <= 16 && S <= cap; ++S) {
+    const double waves = (double)(((long long)ntile * S + slots - 1) / slots) / S;
+    const double cost = waves * (1.0 + 0.004 * (S - 1));
+    if (cost < best_cost - 1e-12) { best_cost = cost; best = S; }
+  }
+  return best;
 }
 
 }  // namespace
@@ -154,7 +164,8 @@ int ormtr_upper(cudaStream_t s, int n, int m, const T* A, int64_t lda, const T* 
     std::vector<GemmParams<T>> hp((size_t)nblk * S);
     for (int b = 0; b < nblk; ++b) {
       const int j0 = b * ib, ibb = (nref - j0 < ib) ? nref - j0 : ib, mi = j0 + ibb;
-      int Sb = mi / 256; Sb = Sb < 1 ? 1 : (Sb > S ? S : Sb);
+      int Sb = bt_splits(m, ibb, (int)sizeof(T), mi / 256 < 1 ? 1 : mi / 256);      // slices of at least 256 rows
+      if (Sb > S) Sb = S;
       const int kc = (((mi + Sb - 1) / Sb) + 15) & ~15;
       Sb = (mi + kc - 1) / kc;
       nsplit[b] = Sb;

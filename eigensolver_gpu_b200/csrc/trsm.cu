@@ -471,7 +471,7 @@ int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h, bool sync
   T* Dinv = (T*)scr;
   int* dinfo = c.d_info + ST_POTRF;
   EIGB_CUDA_CHECK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
-  const int PB = opts().potrf_pb > 0 ? ((opts().potrf_pb + NB - 1) / NB) * NB : 256;
+  const int PB = opts().potrf_pb > 0 ? ((opts().potrf_pb + NB - 1) / NB) * NB : (is_cplx<T>::value ? 192 : 256);
   if (n < 2 * PB || c.stream_hi == nullptr || opts().potrf_pb < 0) {
     if (potrf_rec<T>(s, 0, n, B, ldb, Dinv, dinfo) != 0) return -1;
   } else {

@@ -85,6 +85,11 @@ def bench_hetrd():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gemm"]
+    from eigensolver_gpu_b200._lib import load
+    which = [a for a in sys.argv[1:] if "=" not in a] or ["gemm"]
+    for kv in [a for a in sys.argv[1:] if "=" in a]:          # name=value library options, e.g. gemm_tma=0
+        k, v = kv.split("=")
+        assert load().eigb200_set_option(k.encode(), int(v)) == 0, kv
+        print(f"option {k} = {v}", flush=True)
     for w in which:
         globals()["bench_" + w]()
