@@ -24,6 +24,7 @@ SIGNATURES = {
     "eigb200_mg_alloc": (_i, [C.c_longlong, C.POINTER(C.c_void_p), C.c_char_p]),
     "eigb200_mg_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "eigb200_mg_config": (_i, [_i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_longlong, _p]),
+    "eigb200_mg_flag_bytes": (_i, [_i, _i]),
     "eigb200_mg_unique_id": (_i, [C.c_char_p]),
     "eigb200_mg_init": (_i, [_i, _i, C.c_char_p]),
     "eigb200_mg_finalize": (_i, []),

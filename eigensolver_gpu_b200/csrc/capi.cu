@@ -46,11 +46,14 @@ int eigb200_mg_open(const char* handle64, void** dptr) {
   EIGB_CUDA_CHECK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
   return 0;
 }
+int eigb200_mg_flag_bytes(int n, int world) { return world * mg_flag_stride(n) * (int)sizeof(unsigned long long); }
 int eigb200_mg_config(int rank, int world, void** wbufs, void** flags, long long wbuf_bytes, void* panel_hook) {
   API_BEGIN();
   if (world < 1 || world > 8 || rank < 0 || rank >= world) { set_last_error("eigb200_mg_config: bad rank/world"); return -1; }
   MgConfig& M = mg();
   M.rank = rank; M.P = world; M.wbuf_bytes = wbuf_bytes;
+  // exchange buffers are sized for complex elements: wbuf_bytes = world * 2 * (n + 64) * 16
+  M.flag_stride = world > 0 ? mg_flag_stride((int)(wbuf_bytes / ((long long)world * 32)) - 64) : 0;
   for (int q = 0; q < world; ++q) { M.wbuf[q] = wbufs ? wbufs[q] : nullptr; M.flags[q] = flags ? (unsigned long long*)flags[q] : nullptr; }
   M.hook = (panel_hook_t)panel_hook;
   M.active = world > 1;

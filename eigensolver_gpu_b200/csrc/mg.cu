@@ -106,6 +106,9 @@ void mg_column_range(int ncols, int world, int rank, int& c0, int& c1) {
   c1 = (int)(b1 * align < ncols ? b1 * align : ncols);
 }
 
+// flags per source rank for order <= n: one per 32-row group of the exchanged vector + one for v^H A v (+ slack)
+int mg_flag_stride(int n) { return (n + 31) / 32 + 8; }
+
 int mg_unique_id(char* id128) {
   NcclApi* N = nccl_api();
   if (!N) return -1;
@@ -165,10 +168,12 @@ int mg_ensure_exchange(cudaStream_t s, int n) {
   EIGB_CUDA_CHECK(cudaStreamSynchronize(s));
   mg_release_exchange();
   void *w = nullptr, *f = nullptr;
+  const int fstride = mg_flag_stride(n);
+  const size_t fbytes = (size_t)M.P * fstride * sizeof(unsigned long long);
   EIGB_CUDA_CHECK(cudaMalloc(&w, (size_t)need));
-  EIGB_CUDA_CHECK(cudaMalloc(&f, 4096));
+  EIGB_CUDA_CHECK(cudaMalloc(&f, fbytes));
   EIGB_CUDA_CHECK(cudaMemset(w, 0, (size_t)need));
-  EIGB_CUDA_CHECK(cudaMemset(f, 0, 4096));
+  EIGB_CUDA_CHECK(cudaMemset(f, 0, fbytes));
   struct Handles { cudaIpcMemHandle_t hw, hf; } mine;
   EIGB_CUDA_CHECK(cudaIpcGetMemHandle(&mine.hw, w));
   EIGB_CUDA_CHECK(cudaIpcGetMemHandle(&mine.hf, f));
@@ -188,6 +193,7 @@ int mg_ensure_exchange(cudaStream_t s, int n) {
     M.wbuf[q] = pw; M.flags[q] = (unsigned long long*)pf;
   }
   M.wbuf_bytes = need;
+  M.flag_stride = fstride;
   M.own_exchange = true;
   M.seq = 0;
   return 0;

@@ -37,6 +37,7 @@ struct MgConfig {
   void* wbuf[8] = {nullptr};              // exchange buffers of all ranks (peer-mapped), wbuf[rank] is local
   unsigned long long* flags[8] = {nullptr};
   int64_t wbuf_bytes = 0;                 // size of ONE rank's exchange buffer
+  int flag_stride = 0;                    // flags per source rank in a flag array: one per 32-row group + 1 (v^H A v)
   unsigned long long seq = 0;             // monotonic column sequence number (flags never reset)
   panel_hook_t hook = nullptr;            // legacy (caller-owned communicator): called before every panel to broadcast its columns
   void* comm = nullptr;                   // ncclComm_t created by eigb200_mg_init (library-owned communicator)
@@ -46,6 +47,7 @@ struct MgConfig {
 MgConfig& mg();
 // multi-GPU plumbing (mg.cu)
 void mg_column_range(int ncols, int world, int rank, int& c0, int& c1);
+int mg_flag_stride(int n);
 int mg_unique_id(char* id128);
 int mg_init(int rank, int world, const char* id128);
 int mg_finalize();

@@ -84,7 +84,8 @@ struct TrdP {
   // multi-GPU (1-D block-cyclic distribution of the 64-wide tile columns of the trailing matrix over P ranks)
   int rank, P;                 // P == 1: single GPU
   T* peer_w[8];                // peer_w[q] = rank q's exchange buffer [P][2][wstride] (peer-mapped, NVLink)
-  unsigned long long* peer_flag[8];   // peer_flag[q] = rank q's arrival flags [P]
+  unsigned long long* peer_flag[8];   // peer_flag[q] = rank q's arrival flags [P sources][fstride]: one per 32-row group + [fstride-1] for v^H A v
+  int fstride;                 // flags per source rank
   int64_t wstride;             // elements per exchange slot (>= n + 2)
   unsigned long long seq_base; // sequence number of this panel's first column (flags are monotonic)
 };
@@ -742,17 +743,6 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
   PhaseASmem<T>& S = sm.u.a;
   const unsigned long long seqp = have_prev ? col_seq(p, cprev) : 0ull;
   const unsigned parp = (unsigned)(seqp & 1ull);
-  if (mg && have_prev) {
-    // wait until every rank has delivered its partial w (and v^H A v) of the previous column
-    if (tid < p.P) {
-      const unsigned long long* fl = p.peer_flag[p.rank] + tid;
-      unsigned long long spins = 0;
-      while (ld_acquire_sys(fl) < seqp) {
-        if (++spins > (1ull << 25)) { atomicExch(p.status, 78); __trap(); }
-      }
-    }
-    __syncthreads();
-  }
   // ---- rows [rbeg, rend) of this CTA in groups of 32 (one row per lane); GC = 2^gcs groups run side by side,
   //      each split over WPG = 16 / GC warps
   const int nrows = jp > 0 ? jp : 0;
@@ -763,6 +753,24 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
   const int rbeg = cta * R;
   const int rend = nrows < rbeg + R ? nrows : rbeg + R;
   const int ngrp = rend > rbeg ? (rend - rbeg + 31) >> 5 : 0;
+  if (mg && have_prev) {
+    // wait until every rank has delivered what this CTA reads of the previous column's exchange: the 32-row groups that
+    // cover its rows, the group of row j (scalar warp) and v^H A v -- one flag per (source rank, group), no grid barrier
+    // on the sending side
+    const int gb = rbeg >> 5, ge = rend > rbeg ? (rend - 1) >> 5 : gb - 1;      // groups [gb, ge] (exchange groups are 32-aligned)
+    const int nown = ge - gb + 1;
+    const int nwait = (nown + 2) * p.P;
+    for (int idx = tid; idx < nwait; idx += NTT) {
+      const int q = idx % p.P, k = idx / p.P;
+      const int fi = k < nown ? gb + k : (k == nown ? (j >> 5) : p.fstride - 1);
+      const unsigned long long* fl = p.peer_flag[p.rank] + (int64_t)q * p.fstride + fi;
+      unsigned long long spins = 0;
+      while (ld_acquire_sys(fl) < seqp) {
+        if (++spins > (1ull << 25)) { atomicExch(p.status, 78); __trap(); }
+      }
+    }
+    __syncthreads();
+  }
   const int gcs = ngrp <= 1 ? 0 : (ngrp == 2 ? 1 : 2);
   const int GC = 1 << gcs, wpgs = 4 - gcs, WPG = 1 << wpgs;
   const int grp = warp >> wpgs, sub = warp & (WPG - 1);        // warp 16: grp == GC -> no row work
@@ -1098,7 +1106,9 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
 }
 
 // Phase C (multi-GPU only): reduce this rank's partial sums to one vector w_p(0:j) and push it, together with the
-// local v^H A v, into the exchange buffer of EVERY rank (peer stores over NVLink); the caller then signals.
+// local v^H A v, into the exchange buffer of EVERY rank (peer stores over NVLink).  Every 32-row group is signalled on its
+// own: the warp that pushed a group fences (system scope) and releases one flag per peer, so the receiving CTAs -- which
+// wait only for the groups they read -- need no grid barrier on this side.
 template <typename T>
 __device__ void phase_c(const TrdP<T>& p, int c, PanelSmem<T>& sm, int total_units) {
   const int tid = threadIdx.x;
@@ -1106,43 +1116,63 @@ __device__ void phase_c(const TrdP<T>& p, int c, PanelSmem<T>& sm, int total_uni
   const int j = p.i0 + c;
   if (j <= 0) return;
   const int Tn = (j + TB - 1) / TB, C = strip_len(j, G, p.P, p.upc);
-  const unsigned par = (unsigned)(col_seq(p, c) & 1ull);
-  // groups of 32 rows are dealt to the CTAs; AW warps split the partial-sum slots of a group (L2-latency bound),
-  // warp 0 combines and pushes the 32 values to every rank
+  const unsigned long long seq = col_seq(p, c);
+  const unsigned par = (unsigned)(seq & 1ull);
+  // groups of 32 rows are dealt to the CTAs, two at a time (warps 0-7 / 8-15); the AW warps of a half split the
+  // partial-sum slots of its group (L2-latency bound: four independent loads in flight per lane), its first warp
+  // combines and pushes the 32 values to every rank
   const int lane = tid & 31, warp = tid >> 5;
+  const int half = warp >> 3, wq = warp & (AW - 1);
   const int ngroups = (j + 31) / 32;
-  for (int g = cta; g < ngroups; g += G) {
+  for (int g0 = cta; g0 < ngroups; g0 += 2 * G) {
+    const int g = g0 + half * G;
+    const bool gv = warp < 2 * AW && g < ngroups;
     const int r = g * 32 + lane;
-    const bool rv = r < j;
-    const int I = (g * 32) / TB;
-    int J0 = I + 1;
-    J0 += ((p.rank - J0) % p.P + p.P) % p.P;               // first owned tile column >= I+1
-    const int nd = J0 < Tn ? (Tn - J0 + p.P - 1) / p.P : 0;  // direct slots J0, J0+P, ...
-    const int nt = (I % p.P == p.rank) ? I / C + 1 : 0;      // band slots of an owned tile column
-    if (warp < AW) {
+    const bool rv = gv && r < j;
+    if (gv) {
+      const int I = (g * 32) / TB;
+      int J0 = I + 1;
+      J0 += ((p.rank - J0) % p.P + p.P) % p.P;               // first owned tile column >= I+1
+      const int nd = J0 < Tn ? (Tn - J0 + p.P - 1) / p.P : 0;  // direct slots J0, J0+P, ...
+      const int nt = (I % p.P == p.rank) ? I / C + 1 : 0;      // band slots of an owned tile column
       T sacc = zero_<T>();
       if (rv) {
-        for (int q = warp; q < nd + nt; q += AW) {
-          const T* src = (q < nd) ? (p.Pd + (int64_t)(J0 + q * p.P) * p.ldp) : (p.Pt + (int64_t)(q - nd) * p.ldp);
-          sacc = add_(sacc, ldcg_(src + r));
+        for (int q0 = wq; q0 < nd + nt; q0 += 4 * AW) {
+          T v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int q = q0 + k * AW;
+            const T* src = (q < nd) ? (p.Pd + (int64_t)(J0 + q * p.P) * p.ldp) : (p.Pt + (int64_t)(q - nd) * p.ldp);
+            v[k] = q < nd + nt ? ldcg_(src + r) : zero_<T>();
+          }
+          sacc = add_(sacc, add_(add_(v[0], v[1]), add_(v[2], v[3])));
         }
       }
       sm.u.a.ared[warp * 32 + lane] = sacc;
     }
     __syncthreads();
-    if (warp == 0 && rv) {
-      T tot = zero_<T>();
+    if (gv && wq == 0) {
+      if (rv) {
+        T tot = zero_<T>();
 #pragma unroll
-      for (int w = 0; w < AW; ++w) tot = add_(tot, sm.u.a.ared[w * 32 + lane]);
-      for (int q = 0; q < p.P; ++q) ex_slot(p, q, p.rank, par)[r] = tot;
+        for (int w = 0; w < AW; ++w) tot = add_(tot, sm.u.a.ared[(half * AW + w) * 32 + lane]);
+        for (int q = 0; q < p.P; ++q) ex_slot(p, q, p.rank, par)[r] = tot;
+      }
+      __threadfence_system();
+      __syncwarp();
+      if (lane < p.P) st_release_sys(p.peer_flag[lane] + (int64_t)p.rank * p.fstride + g, seq);
     }
     __syncthreads();
   }
-  if (cta == 0) {
+  if (cta == G - 1) {       // (the last CTA has the fewest groups)
     double vv = 0.0;
     for (int t = tid; t < total_units; t += NTT) vv += __ldcg(p.vavunit + t);
     vv = block_sum<double>(vv, sm.dscal);
-    if (tid < p.P) ex_slot(p, tid, p.rank, par)[p.wstride - 1] = from_real<T>(vv);
+    if (tid < p.P) {
+      ex_slot(p, tid, p.rank, par)[p.wstride - 1] = from_real<T>(vv);
+      __threadfence_system();
+      st_release_sys(p.peer_flag[tid] + (int64_t)p.rank * p.fstride + p.fstride - 1, seq);
+    }
   }
 }
 
@@ -1173,13 +1203,7 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
     target += gridDim.x;
     grid_barrier(p.barrier, target, p.status, false, []() {});
     if (MG && p.P > 1 && p.i0 + c > 0) {
-      phase_c<T>(p, c, sm, total_units);
-      target += gridDim.x;
-      grid_barrier(p.barrier, target, p.status, true, []() {});     // system-scope fences: peer stores are complete
-      if (blockIdx.x == 0 && threadIdx.x < p.P) {
-        __threadfence_system();
-        st_release_sys(p.peer_flag[threadIdx.x] + p.rank, col_seq(p, c));
-      }
+      phase_c<T>(p, c, sm, total_units);        // (signals per 32-row group: no third grid barrier)
     }
     stamp(c, 4);
   }
@@ -1333,6 +1357,8 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     p.wstride = M.wbuf_bytes / ((int64_t)M.P * 2 * (int64_t)sizeof(T));
     if (p.wstride < (int64_t)n + 2) { set_last_error("hetrd: multi-GPU exchange buffer too small"); return -1; }
     for (int q = 0; q < M.P; ++q) { p.peer_w[q] = (T*)M.wbuf[q]; p.peer_flag[q] = M.flags[q]; }
+    p.fstride = M.flag_stride;
+    if (p.fstride < (n + 31) / 32 + 2) { set_last_error("hetrd: multi-GPU flag array too small"); return -1; }
     // parameter blocks of the per-tile-column rank-2k updates of ALL panels: built once, uploaded once (no host
     // synchronisation inside the panel loop)
     const size_t ntc = (size_t)(n / TB + 2);

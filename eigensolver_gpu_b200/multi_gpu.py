@@ -128,9 +128,8 @@ class HetrdExchange:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        es = 16 if cplx else 8
-        self.wbytes = self.world * 2 * (n + 64) * es
-        fbytes = 4096
+        self.wbytes = self.world * 2 * (n + 64) * 16          # always sized for complex elements
+        fbytes = self.lib.eigb200_mg_flag_bytes(n, self.world)
         wptr, fptr = C.c_void_p(), C.c_void_p()
         wh, fh = C.create_string_buffer(64), C.create_string_buffer(64)
         check(self.lib.eigb200_mg_alloc(self.wbytes, C.byref(wptr), wh), "mg_alloc")

@@ -47,6 +47,9 @@ int eigb200_get_option(const char* name);
 int eigb200_mg_alloc(long long bytes, void** dptr, char* handle64);
 int eigb200_mg_open(const char* handle64, void** dptr);
 int eigb200_mg_config(int rank, int world, void** wbufs, void** flags, long long wbuf_bytes, void* panel_hook);
+/* size of one rank's flag array for order n (one flag per source rank and 32-row group); exchange buffers are always sized
+ * for complex elements: wbuf_bytes = world * 2 * (n + 64) * 16 */
+int eigb200_mg_flag_bytes(int n, int world);
 /* Library-owned communicator (what a Fortran/MPI caller uses; the functions above remain for callers that own the
  * communicator themselves).  Rendezvous: rank 0 calls eigb200_mg_unique_id (ncclGetUniqueId), the caller distributes the
  * 128 bytes (MPI_Bcast, torch.distributed, a file ...), then EVERY rank calls eigb200_mg_init with the device it will
