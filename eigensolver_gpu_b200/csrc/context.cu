@@ -187,6 +187,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "mg_switch_n")) { o.mg_switch_n = value; return 0; }
   if (!strcmp(name, "mg_dist_min_n")) { o.mg_dist_min_n = value; return 0; }
   if (!strcmp(name, "mg_gather_z")) { o.mg_gather_z = value; return 0; }
+  if (!strcmp(name, "mg_potrf_min_n")) { o.mg_potrf_min_n = value; return 0; }
   if (!strcmp(name, "verbose")) { ctx().verbose = value; return 0; }
   return -1;
 }
@@ -207,6 +208,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "mg_switch_n")) return o.mg_switch_n;
   if (!strcmp(name, "mg_dist_min_n")) return o.mg_dist_min_n;
   if (!strcmp(name, "mg_gather_z")) return o.mg_gather_z;
+  if (!strcmp(name, "mg_potrf_min_n")) return o.mg_potrf_min_n;
   if (!strcmp(name, "verbose")) return ctx().verbose;
   return -1;
 }

@@ -30,6 +30,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -54,6 +55,7 @@ NcclApi* nccl_api() {
   EIGB_SYM(CommDestroy, "ncclCommDestroy")
   EIGB_SYM(Broadcast, "ncclBroadcast")
   EIGB_SYM(AllGather, "ncclAllGather")
+  EIGB_SYM(AllReduce, "ncclAllReduce")
   EIGB_SYM(GroupStart, "ncclGroupStart")
   EIGB_SYM(GroupEnd, "ncclGroupEnd")
   EIGB_SYM(GetErrorString, "ncclGetErrorString")
@@ -223,6 +225,30 @@ int mg_bcast_columns(cudaStream_t s, void* A, int64_t ld, int c0, int nc, int ow
   return 0;
 }
 
+// plain pieces for stage code that packs its own buffers (distributed Cholesky): broadcast of a contiguous buffer, NCCL
+// group brackets, max-reduction of one device int (status words)
+int mg_bcast(cudaStream_t s, void* ptr, size_t bytes, int root) {
+  MgConfig& M = mg();
+  NcclApi* N = nccl_api();
+  if (!N || !M.comm) return -1;
+  if (bytes == 0) return 0;
+  EIGB_NCCL_CHECK(N->Broadcast(ptr, ptr, bytes, ncclChar, root, (ncclComm_t)M.comm, s));
+  return 0;
+}
+int mg_group(bool start) {
+  NcclApi* N = nccl_api();
+  if (!N) return -1;
+  EIGB_NCCL_CHECK(start ? N->GroupStart() : N->GroupEnd());
+  return 0;
+}
+int mg_allreduce_max_int(cudaStream_t s, int* dptr) {
+  MgConfig& M = mg();
+  NcclApi* N = nccl_api();
+  if (!N || !M.comm) return -1;
+  EIGB_NCCL_CHECK(N->AllReduce(dptr, dptr, 1, ncclInt32, ncclMax, (ncclComm_t)M.comm, s));
+  return 0;
+}
+
 // every rank owns the contiguous column block mg_column_range(ncols, P, rank) of the ld x ncols matrix; after the call
 // all ranks hold all blocks (in place; one NCCL group of P broadcasts)
 int mg_allgather_columns(cudaStream_t s, void* A, int64_t ld, int ncols, int elem_bytes) {
@@ -272,9 +298,11 @@ int hegvdx_mg_driver(int n, T* A, int lda, T* B, int ldb, T* Z, int ldz, int il,
   const int min_n = opts().mg_dist_min_n >= 0 ? opts().mg_dist_min_n : (P <= 2 ? 6144 : 4096);
   const bool dist_trd = n >= min_n;
   if (dist_trd) EIGB_MG_FAIL(mg_ensure_exchange(s, n) != 0, "exchange buffer setup");
-  // 1. Cholesky, replicated (deterministic => identical U everywhere)
+  // 1. Cholesky: block columns dealt cyclically over the ranks from mg_potrf_min_n on (trsm.cu, potrf_upper_mg), else
+  //    replicated (deterministic => identical U everywhere)
   prof_begin(PROF_POTRF, s);
-  int rc = potrf_upper<T>(s, n, B, ldb, nullptr, /*sync_status=*/false);
+  int rc = (opts().mg_potrf_min_n >= 0 && n >= opts().mg_potrf_min_n) ? potrf_upper_mg<T>(s, n, B, ldb)
+                                                                       : potrf_upper<T>(s, n, B, ldb, nullptr, /*sync_status=*/false);
   prof_end(PROF_POTRF, s);
   EIGB_MG_FAIL(rc != 0, "potrf");
   // 2. C = U^-H A U^-1 by two column-parallel left solves: Y = U^-H A on this rank's columns, exchange, then

@@ -17,6 +17,7 @@ struct Options {
   int trd_coop = 1;     // persistent cooperative panel kernel (0: one launch per phase)
   int mg_switch_n = 3072; // multi-GPU hetrd: below this trailing order all ranks continue replicated
   int mg_dist_min_n = -1; // multi-GPU driver: distribute the tridiagonalization from this order on (-1: 6144 for 2 ranks, else 4096)
+  int mg_potrf_min_n = 4096; // multi-GPU driver: distribute the Cholesky factorization from this order on (-1: always replicated)
   int mg_gather_z = 1;    // multi-GPU driver: gather the eigenvector column blocks so that every rank holds Z(:, 1:m)
   int trd_upc = 3;      // tile engine: target number of tile units per CTA (strip length heuristic)
   int trd_prefetch = 0; // tiles per CTA prefetched into L2 during phase A (-1: 256 KB worth, 0: off -- no gain measured)
@@ -54,6 +55,9 @@ int mg_finalize();
 int mg_ensure_exchange(cudaStream_t s, int n);
 int mg_bcast_columns(cudaStream_t s, void* A, int64_t ld, int c0, int nc, int owner, int elem_bytes);
 int mg_allgather_columns(cudaStream_t s, void* A, int64_t ld, int ncols, int elem_bytes);
+int mg_bcast(cudaStream_t s, void* ptr, size_t bytes, int root);
+int mg_group(bool start);
+int mg_allreduce_max_int(cudaStream_t s, int* dptr);
 }
 #include <vector>
 namespace eigb200 {
@@ -81,6 +85,9 @@ template <typename T> int symmetrize_from_upper(cudaStream_t s, int n, T* A, int
 template <typename T> int restore_lower(cudaStream_t s, int n, T* A, int64_t lda, const T* save, int64_t lds);
 // sync_status = false: *info_h is not written, the pivot index stays in ctx().d_info[ST_POTRF]
 template <typename T> int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h, bool sync_status = true);
+// distributed variant (collective over the ranks of eigb200_mg_init): B replicated on entry, U replicated on exit, pivot
+// status max-reduced into ctx().d_info[ST_POTRF] on every rank
+template <typename T> int potrf_upper_mg(cudaStream_t s, int n, T* B, int64_t ldb);
 template <typename T>
 int trsm_upper(cudaStream_t s, char side, char trans, int m, int n, const T* U, int64_t ldu, T* B, int64_t ldb);
 template <typename T>

@@ -532,6 +532,87 @@ int potrf_upper(cudaStream_t s, int n, T* B, int64_t ldb, int* info_h, bool sync
   return 0;
 }
 
+// pack / unpack of a row block of a column-major matrix:  P(0:kb, c) <-> A(r0:r0+kb, c0 + c),  c in [0, nc)
+template <typename T>
+__global__ void rowblock_copy_kernel(T* A, int64_t lda, int r0, int kb, int c0, int nc, T* P, int64_t ldp, int to_matrix) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r >= kb || c >= nc) return;
+  T* a = A + (r0 + r) + (int64_t)(c0 + c) * lda;
+  T* q = P + r + (int64_t)c * ldp;
+  if (to_matrix) *a = *q; else *q = *a;
+}
+
+// Distributed Cholesky (multi-GPU drivers): right-looking by MB-wide block columns dealt cyclically over the ranks.
+//   step k: owner factors the diagonal block and broadcasts block column k; every rank inverts the 64x64 diagonal
+//           blocks it needs, solves the row panel U_kj = U_kk^-H A_kj on ITS block columns j > k, the panel pieces are
+//           packed, all-gathered (one NCCL group) and unpacked, then every rank updates ITS block columns
+//           A(k+1:j, j) -= U_k,(k+1:j)^H U_kj  (one rank-MB update per owned block column, upper part only).
+// U ends up complete on every rank (the later stages need all of it).  The pivot status is max-reduced.
+template <typename T>
+int potrf_upper_mg(cudaStream_t s, int n, T* B, int64_t ldb) {
+  MgConfig& M = mg();
+  if (M.comm == nullptr || M.P <= 1) return potrf_upper<T>(s, n, B, ldb, nullptr, false);
+  if (n <= 0) return 0;
+  if (enable_all_smem<T>() != 0) return -1;
+  Context& c = ctx();
+  const int P = M.P, rank = M.rank;
+  const int MB = 512;
+  const int nblk64 = cdiv(n, NB), nbk = cdiv(n, MB);
+  const size_t dinv_elems = (size_t)nblk64 * NB * NB;
+  void* scr = ctx_scratch((dinv_elems + (size_t)MB * n) * sizeof(T) + 1024);
+  if (!scr) return -1;
+  Arena ar(scr, c.scratch_bytes);
+  T* Dinv = ar.take<T>(dinv_elems);
+  T* Pk = ar.take<T>((size_t)MB * n);                 // packed row panel U_k* (kb x r, ld = MB)
+  if (!Pk) { set_last_error("potrf (multi-GPU): scratch arena too small"); return -1; }
+  int* dinfo = c.d_info + ST_POTRF;
+  EIGB_CUDA_CHECK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
+  TriInv<T> ti; ti.d64 = Dinv;
+  const int es = (int)sizeof(T);
+  for (int k = 0; k < nbk; ++k) {
+    const int k0 = k * MB, kb = n - k0 < MB ? n - k0 : MB, own = k % P;
+    if (rank == own) { if (potrf_rec<T>(s, k0, k0 + kb, B, ldb, Dinv, dinfo) != 0) return -1; }
+    if (mg_bcast_columns(s, B, ldb, k0, kb, own, es) != 0) return -1;
+    const int r0 = k0 + kb, r = n - r0;
+    if (r <= 0) break;
+    if (rank != own) {      // inverted 64x64 diagonal blocks of U_kk (the owner has them from its factorization)
+      trtri_blocks_kernel<T><<<dim3(cdiv(kb, NB), 8), 256, tri_smem<T>(), s>>>(B, ldb, k0 + kb, Dinv, k0 / NB);
+      EIGB_LAUNCH_CHECK();
+    }
+    // row panel on this rank's block columns, packed into Pk
+    for (int j = k + 1; j < nbk; ++j) {
+      if (j % P != rank) continue;
+      const int j0 = j * MB, wj = n - j0 < MB ? n - j0 : MB;
+      if (trsm_rec<T>(s, 'L', 'C', k0, k0 + kb, wj, B, ldb, B + (int64_t)j0 * ldb, ldb, ti) != 0) return -1;
+      rowblock_copy_kernel<T><<<dim3(cdiv(kb, 64), cdiv(wj, 4)), dim3(64, 4), 0, s>>>(B, ldb, k0, kb, j0, wj, Pk + (int64_t)(j0 - r0) * MB, MB, 0);
+      EIGB_LAUNCH_CHECK();
+    }
+    if (mg_group(true) != 0) return -1;
+    for (int j = k + 1; j < nbk; ++j) {
+      const int j0 = j * MB, wj = n - j0 < MB ? n - j0 : MB;
+      if (mg_bcast(s, Pk + (int64_t)(j0 - r0) * MB, (size_t)wj * MB * es, j % P) != 0) { mg_group(false); return -1; }
+    }
+    if (mg_group(false) != 0) return -1;
+    // the complete row panel goes back into B (U must be complete everywhere); pieces this rank solved are already there
+    rowblock_copy_kernel<T><<<dim3(cdiv(kb, 64), cdiv(r, 4)), dim3(64, 4), 0, s>>>(B, ldb, k0, kb, r0, r, Pk, MB, 1);
+    EIGB_LAUNCH_CHECK();
+    // trailing update of this rank's block columns: rows r0 .. j0+wj (upper part of the diagonal block)
+    for (int j = k + 1; j < nbk; ++j) {
+      if (j % P != rank) continue;
+      const int j0 = j * MB, wj = n - j0 < MB ? n - j0 : MB;
+      GemmParams<T> p{};
+      p.M = j0 + wj - r0; p.N = wj; p.nseg = 1;
+      p.A[0] = Pk; p.lda[0] = MB; p.B[0] = Pk + (int64_t)(j0 - r0) * MB; p.ldb[0] = MB; p.K[0] = kb;
+      p.A[1] = p.A[0]; p.lda[1] = MB; p.B[1] = p.B[0]; p.ldb[1] = MB; p.K[1] = 0;
+      p.sa[0] = p.sa[1] = -1.0; p.sb[0] = p.sb[1] = 1.0;
+      p.C = B + r0 + (int64_t)j0 * ldb; p.ldc = ldb; p.alpha = -1.0; p.beta = 1.0;
+      p.mode = 1; p.real_diag = 1; p.colmap = nullptr; p.diag_off = j0 - r0;
+      if (gemm_launch<T>(s, true, true, p) != 0) return -1;
+    }
+  }
+  return mg_allreduce_max_int(s, dinfo);
+}
+
 // Triangular solves with the upper-triangular U (n_u x n_u):
 //   side 'L', trans 'N':  B (n_u x ncols) <- U^-1  B
 //   side 'L', trans 'C':  B (n_u x ncols) <- U^-H  B
@@ -595,6 +676,7 @@ int hegst_upper(cudaStream_t s, int n, T* A, int64_t lda, const T* U, int64_t ld
   template int symmetrize_from_upper<T>(cudaStream_t, int, T*, int64_t, T*, int64_t);                    \
   template int restore_lower<T>(cudaStream_t, int, T*, int64_t, const T*, int64_t);                      \
   template int potrf_upper<T>(cudaStream_t, int, T*, int64_t, int*, bool);                                  \
+  template int potrf_upper_mg<T>(cudaStream_t, int, T*, int64_t);                                  \
   template int trsm_upper<T>(cudaStream_t, char, char, int, int, const T*, int64_t, T*, int64_t);        \
   template int hegst_upper<T>(cudaStream_t, int, T*, int64_t, const T*, int64_t, T*, int64_t);
 EIGB_INST(double)

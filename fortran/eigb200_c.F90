@@ -51,6 +51,44 @@ module eigb200_c
       integer(c_int)        :: info
     end function eigb200_zheevd
 
+    ! ---- multi-GPU (one MPI rank per GPU, ONE problem): include/eigb200.h, "library-owned communicator" ----------------
+    ! rank 0: eigb200_mg_unique_id(id); MPI_Bcast(id, 128, MPI_BYTE, 0, comm); every rank: eigb200_mg_init(rank, nranks, id)
+    integer(c_int) function eigb200_mg_unique_id(id128) bind(C, name="eigb200_mg_unique_id")
+      import :: c_int, c_char
+      character(kind=c_char), dimension(128) :: id128
+    end function eigb200_mg_unique_id
+
+    integer(c_int) function eigb200_mg_init(rank, world, id128) bind(C, name="eigb200_mg_init")
+      import :: c_int, c_char
+      integer(c_int), value :: rank, world
+      character(kind=c_char), dimension(128) :: id128
+    end function eigb200_mg_init
+
+    integer(c_int) function eigb200_mg_finalize() bind(C, name="eigb200_mg_finalize")
+      import :: c_int
+    end function eigb200_mg_finalize
+
+    integer(c_int) function eigb200_dsygvdx_mg(n, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, work_h, lwork_h, &
+                                               iwork_h, liwork_h, Z_h, ldz_h, w_h, info, skip_host_copy) &
+                                               bind(C, name="eigb200_dsygvdx_mg")
+      import :: c_int, c_ptr, c_devptr
+      integer(c_int), value :: n, lda, ldb, ldz, il, iu, lwork, lwork_h, liwork_h, ldz_h, skip_host_copy
+      type(c_devptr), value :: A, B, Z, w, work
+      type(c_ptr), value    :: work_h, iwork_h, Z_h, w_h
+      integer(c_int)        :: info
+    end function eigb200_dsygvdx_mg
+
+    integer(c_int) function eigb200_zhegvdx_mg(n, A, lda, B, ldb, Z, ldz, il, iu, w, work, lwork, rwork, lrwork, &
+                                               work_h, lwork_h, rwork_h, lrwork_h, iwork_h, liwork_h, Z_h, ldz_h, w_h, &
+                                               info, skip_host_copy) bind(C, name="eigb200_zhegvdx_mg")
+      import :: c_int, c_ptr, c_devptr
+      integer(c_int), value :: n, lda, ldb, ldz, il, iu, lwork, lrwork, lwork_h, lrwork_h, liwork_h, ldz_h
+      integer(c_int), value :: skip_host_copy
+      type(c_devptr), value :: A, B, Z, w, work, rwork
+      type(c_ptr), value    :: work_h, rwork_h, iwork_h, Z_h, w_h
+      integer(c_int)        :: info
+    end function eigb200_zhegvdx_mg
+
     ! optional: stream the solver issues its work on / one-shot "A has been uploaded" event (include/eigb200.h)
     integer(c_int) function eigb200_set_stream(stream) bind(C, name="eigb200_set_stream")
       import :: c_int, cuda_stream_kind

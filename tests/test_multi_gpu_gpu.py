@@ -125,6 +125,7 @@ def _worker_cabi(rank, world, port, cplx, n, il, iu, out):
     lib = load()
     MG.mg_init()
     assert lib.eigb200_set_option(b"mg_dist_min_n", 0) == 0 and lib.eigb200_set_option(b"mg_switch_n", 256) == 0
+    assert lib.eigb200_set_option(b"mg_potrf_min_n", 0) == 0         # distributed Cholesky whatever the order
     a, b = matgen.family_c(n, cplx, seed=5)
     ad, bd = S.to_dev(np.triu(a)), S.to_dev(np.triu(b))
     info, w, z, ws = api.solve_generalized_mg(ad, bd, il, iu, skip_host_copy=False)
