@@ -17,7 +17,8 @@ struct Options {
   int trd_coop = 1;     // persistent cooperative panel kernel (0: one launch per phase)
   int mg_switch_n = 3072; // multi-GPU hetrd: below this trailing order all ranks continue replicated
   int mg_dist_min_n = -1; // multi-GPU driver: distribute the tridiagonalization from this order on (-1: 6144 for 2 ranks, else 4096)
-  int mg_potrf_min_n = 4096; // multi-GPU driver: distribute the Cholesky factorization from this order on (-1: always replicated)
+  int mg_potrf_min_n = 20000; // multi-GPU driver: distribute the Cholesky factorization from this order on (-1: always replicated;
+                              // below, the look-ahead single-GPU factorization replicated on every rank is faster)
   int mg_gather_z = 1;    // multi-GPU driver: gather the eigenvector column blocks so that every rank holds Z(:, 1:m)
   int trd_upc = 3;      // tile engine: target number of tile units per CTA (strip length heuristic)
   int trd_prefetch = 0; // tiles per CTA prefetched into L2 during phase A (-1: 256 KB worth, 0: off -- no gain measured)

@@ -72,6 +72,7 @@ struct TrdP {
   double* vavunit;             // [units] partial v^H A v, one slot per tile unit (deterministic whatever CTA ran it)
   T* alpha_slot;               // a(j-1, j) before scaling
   T* scale_slot;               // 1 / (alpha - beta) of the latest reflector
+  double* beta_slot;           // [0] beta of the latest reflector, [1] the stored diagonal element A(j-1, j-1) its product saw
   unsigned* barrier;
   unsigned* qctr;              // [NBMAX] tile-unit queue heads, one per panel column (zeroed per panel)
   int* status;
@@ -118,7 +119,7 @@ struct PhaseASmem {
   T z1[NBMAX], z2[NBMAX], rowV[NBMAX], rowW[NBMAX];
   T ared[NW * 32 * 2];   // per-warp slices of (wraw - t1, t2) for the rows in flight
   T s_tau, s_scale, s_wj;   // scalars of the previous reflector, from the scalar warp
-  double s_alpha;
+  double s_alpha, s_beta;   // alpha' and beta of the previous reflector
 };
 // phase A and the tile engine never run at the same time: their scratch is overlaid
 template <typename T>
@@ -134,7 +135,6 @@ struct PanelSmem {
   uint64_t full[8], empty[8];   // ring mbarriers
   TileMeta meta[8];
   ColDesc cd[2];                // descriptors of the current and the next product (parity of the panel column)
-  T hh_scale;                   // phase B: alpha - beta (= x~(j-1)) from warp 0
 };
 
 __device__ __forceinline__ double ldcg_(const double* p) { return __ldcg(p); }
@@ -188,8 +188,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int
   __syncthreads();
   if (threadIdx.x == 0) {
     hook();                      // last per-CTA global stores of the phase (e.g. the partial norm)
-    if (sys) __threadfence_system(); else __threadfence();
-    atomicAdd(bar, 1u);
+    // arrive: a release reduction (no return value to wait for; cumulative over the CTA's stores through the bar.sync above)
+    if (sys) { __threadfence_system(); atomicAdd(bar, 1u); }
+    else asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" :: "l"(bar) : "memory");
     unsigned long long spins = 0;
     while (true) {
       unsigned v;
@@ -197,7 +198,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int
       if (v >= target) break;
       if (++spins > (1ull << 25)) { atomicExch(status, 77); __trap(); }   // watchdog: never hang the GPU
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -546,11 +546,13 @@ __device__ __forceinline__ void process_tiles(ConsumerState<T>& cs, const int4 (
 
 // XR: (global index r, raw x value) -> x(r) (must return 0 for r >= n); xsrc: x stored with at least
 // roundup64(n) readable entries.  All NTT threads must call; ends with a CTA barrier.
-template <typename T, class XR>
+// PH: called once by the producer warp (all 32 lanes) after its first ring-full of tile fetches is in flight (or at
+// the end if it had fewer): work that must happen during the tile phase without holding up anybody's tiles.
+template <typename T, class XR, class PH>
 __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc,
                            XR xfix, T* Pd, T* Pt, int64_t ldp, double* vavunit, unsigned* qctr, int cta, int G, bool tma,
                            T* ring, uint64_t* full, uint64_t* empty, TileMeta* meta, RingState& rs, EngineSmem<T>& es,
-                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc, int upc) {
+                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc, int upc, PH producer_hook) {
   constexpr int S = RingCfg<T>::STAGES, NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int st = rs.stage;
@@ -566,6 +568,7 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol_stream));
     }
     int unit = cta;                       // first unit static, the following ones from the queue
+    int issued = 0;
     for (;;) {
       const bool end = unit >= um.total;
       int J = 0, I0 = 0, I1 = 0; bool hd = false;
@@ -603,10 +606,12 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
           else if (lane == NBOX + 1) bulk_copy_g2s(dst + TB * TB + TB, xsrc + J * TB, (unsigned)(TB * sizeof(T)), &full[st]);
         }
         st = (st + 1) % S;
+        if (!end && ++issued == S) producer_hook();
       }
       if (end) break;
       unit = __shfl_sync(0xffffffffu, nu, 0);
     }
+    if (issued < S) producer_hook();
     // idle from here on: derive the next product's descriptor while the consumers drain the ring
     if (lane == 0 && next_cd != nullptr) compute_desc(*next_cd, jnext, G, Pdesc, upc);
   } else {
@@ -704,7 +709,7 @@ __global__ void __launch_bounds__(NTT, 1) hemv_tiles_kernel(const __grid_constan
   auto xfix = [n](int r, T raw) -> T { return r < n ? raw : zero_<T>(); };
   const UnitMap um = engine_prepare<T>(n, C, 0, 1, es);
   engine_run<T>(um, A, lda, n, xpad, xfix, Pd, Pt, ldp, vavunit, qctr, blockIdx.x, gridDim.x, tma != 0, ring, full, empty,
-                meta, rs, es, &tmap, nullptr, 0, 1, 6);
+                meta, rs, es, &tmap, nullptr, 0, 1, 6, []() {});
 }
 template <typename T>
 __global__ void hemv_reduce_kernel(const T* Pd, const T* Pt, int64_t ldp, int n, int C, T* y) {
@@ -789,14 +794,17 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
       if (round == 0 && have_prev) {
         const T tau_p = ldcg_(p.tau + j);        // written by CTA 0 in the previous phase B (before a barrier)
         const T scale_p = ldcg_(p.scale_slot);
+        const double beta_p = __ldcg(p.beta_slot), ajj_p = __ldcg(p.beta_slot + 1);
         T a1[4], a2[4], a3[4], a4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int cc = cprev + 1 + lane + 32 * k;
           a1[k] = a2[k] = a3[k] = a4[k] = zero_<T>();
           if (cc < nbp) {
-            a1[k] = mul_(scale_p, ldcg_(p.zfin + cc)); a2[k] = mul_(scale_p, ldcg_(p.zfin + NBMAX + cc));   // z = scale * (.)^H x~
             a3[k] = ldcg_(p.A + j + (int64_t)(p.i0 + cc) * p.lda); a4[k] = ldcg_(p.W + j + (int64_t)cc * p.ldw);
+            // z = scale * (.)^H x~ = scale * ((.)^H x - beta conj(row j of (.)))
+            a1[k] = mul_(scale_p, sub_(ldcg_(p.zfin + cc), scale_(conj_(a3[k]), beta_p)));
+            a2[k] = mul_(scale_p, sub_(ldcg_(p.zfin + NBMAX + cc), scale_(conj_(a4[k]), beta_p)));
           }
         }
         // partial-sum slots of row j (or the P exchange slots)
@@ -836,7 +844,8 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
         }
         zz = warp_sum(zz);
         part = warp_sum(part);
-        wj = mul_(scale_p, warp_sum(wj));         // (A v)(j) = scale * (A x~)(j)
+        const T wj_raw = warp_sum(wj);            // (A x)(j)
+        wj = mul_(scale_p, sub_(wj_raw, from_real<T>(beta_p * ajj_p)));    // (A v)(j) = scale * ((A x)(j) - beta A(j,j))
         vx = warp_sum(vx);
         __syncthreads();                          // (#1) workers' shares of x~^H A x~ are in dscal
         double vv = vx;
@@ -844,12 +853,13 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
 #pragma unroll
           for (int w = 0; w < NW; ++w) vv += sm.dscal[w];
         }
+        vv += beta_p * (beta_p * ajj_p - 2.0 * real_(wj_raw));     // x~^H A x~ from x^H A x
         vv *= abs2_(scale_p);                     // v^H A v = |scale|^2 x~^H A x~
         // rho = v^H A v - 2 Re(z1^H z2), alpha' = -1/2 |tau|^2 rho, W(j, c+1) = tau (w_j - part) + alpha' (v(j) = 1)
         const double rho = vv - 2.0 * zz;
         const double alpha_p = -0.5 * abs2_(tau_p) * rho;
         if (lane == 0) {
-          S.s_tau = tau_p; S.s_scale = scale_p; S.s_alpha = alpha_p;
+          S.s_tau = tau_p; S.s_scale = scale_p; S.s_alpha = alpha_p; S.s_beta = beta_p;
           S.s_wj = add_(mul_(tau_p, sub_(wj, part)), from_real<T>(alpha_p));
         }
       } else if (round == 0) {
@@ -881,7 +891,7 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
     // ===================== worker warps =====================
     if (rv && sub == 0) {
       if (have_prev) xb = ldcg_(p.xbuf + r);
-      if (c >= 0) acol = ldcg_(p.A + r + (int64_t)j * p.lda);
+      if (c >= 0 || have_prev) acol = ldcg_(p.A + r + (int64_t)j * p.lda);      // (also the correction column of the product)
     }
     const T scale_w = have_prev ? ldcg_(p.scale_slot) : zero_<T>();
     if (have_prev) {
@@ -979,6 +989,8 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
       if (have_prev) {
         const T tau_p = S.s_tau, scale_p = S.s_scale, wjfin = S.s_wj;
         const double alpha_p = S.s_alpha;
+        // the product ran on the raw column: (A x~)(r) = (A x)(r) - beta A(r, j)   (rows r < j; row j comes from the scalar warp)
+        if (r < j) u = sub_(u, mul_(scale_p, scale_(acol, S.s_beta)));
         // the reflector generated in the previous phase B: v(r) = scale * x(r), v(j) = 1
         const T vnew = (r == j) ? from_real<T>(1.0) : mul_(scale_p, xb);
         p.A[r + (int64_t)(j + 1) * p.lda] = vnew;
@@ -992,6 +1004,7 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
           a = from_real<T>(real_(a));
           p.d[j] = real_(a);
           p.A[j + (int64_t)j * p.lda] = a;
+          p.xbuf[j] = zero_<T>();       // x is zero from row j on (the tile engine reads whole 64-row slices)
         } else {
           p.xbuf[r] = a;
           if (r < j - 1) nrm += abs2_(a);
@@ -1037,36 +1050,32 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
   um.rcpC = cd.rcpC;
   // cache hints only while the triangle of this product exceeds what L2 can hold anyway
   um.keepI = ((int64_t)cd.Tn * cd.Tn * (int64_t)(TB * TB * sizeof(T) / 2) > ((int64_t)96 << 20)) ? p.keepI : 0;
-  // The product runs on the UNSCALED column x~ (x~(j-1) = alpha - beta, so that v = scale * x~ with
-  // scale = 1 / (alpha - beta)): no multiplication per element in the tile loop; the consumers of the partial sums
-  // (phase A) apply scale, |scale|^2 once per row / scalar.
-  T scale = from_real<T>(1.0);
-  T xt = zero_<T>();
-  if (warp < NW) {
-    if (warp == 0) {
-      double xs[5];
+  // The product runs on the RAW updated column x (x(j-1) = alpha), not on the Householder vector: with
+  //   x~ = x - beta e_(j-1)   (so that v = scale * x~, scale = 1 / (alpha - beta)),
+  // A x~ = A x - beta A(:, j-1),  x~^H A x~ = x^H A x - 2 beta Re (A x)(j-1) + beta^2 A(j-1, j-1)  and
+  // V^H x~ = V^H x - beta conj(V(j-1, :)).  The consumers of the partial sums (the next phase A) apply these rank-one
+  // corrections and the scale once per row / scalar -- column j-1 of A is the very column they load anyway.  Nothing in
+  // the tile phase therefore waits for the Householder scalars: beta, tau, scale are formed by the producer warp of CTA 0
+  // once its first ring-full of tiles is in flight (fixed summation order; every CTA reads them back after the barrier).
+  auto scalars_hook = [&]() {
+    if (cta != 0) return;
+    double xs[5];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) { const int g = lane + 32 * k; xs[k] = g < G ? __ldcg(p.npart + g) : 0.0; }
-      const T alpha = ldcg_(p.alpha_slot);
-      double x2 = ((xs[0] + xs[1]) + (xs[2] + xs[3])) + xs[4];
-      for (int g = lane + 160; g < G; g += 32) x2 += __ldcg(p.npart + g);
-      x2 = warp_sum(x2);
-      double beta; T tau;
-      larfg_scalars(alpha, x2, beta, tau, scale);
-      if (lane == 0) {
-        sm.hh_scale = sub_(alpha, from_real<T>(beta));
-        if (cta == 0) { p.e[j - 1] = beta; p.tau[j - 1] = tau; *p.scale_slot = scale; }
-      }
+    for (int k = 0; k < 5; ++k) { const int g = lane + 32 * k; xs[k] = g < G ? __ldcg(p.npart + g) : 0.0; }
+    const T alpha = ldcg_(p.alpha_slot);
+    const double ajj = real_(ldcg_(p.A + (j - 1) + (int64_t)(j - 1) * p.lda));     // stored diagonal the tiles see
+    double x2 = ((xs[0] + xs[1]) + (xs[2] + xs[3])) + xs[4];
+    for (int g = lane + 160; g < G; g += 32) x2 += __ldcg(p.npart + g);
+    x2 = warp_sum(x2);
+    double beta; T tau, scale;
+    larfg_scalars(alpha, x2, beta, tau, scale);
+    if (lane == 0) {
+      p.e[j - 1] = beta; p.tau[j - 1] = tau; *p.scale_slot = scale;
+      p.beta_slot[0] = beta; p.beta_slot[1] = ajj;
     }
-    consumer_barrier();
-    xt = sm.hh_scale;
-  }
-  tstamp(p, c, 12);
-  auto xfix = [j, xt](int r, T raw) -> T {
-    if (r >= j) return zero_<T>();
-    if (r == j - 1) return xt;
-    return raw;
   };
+  tstamp(p, c, 12);
+  auto xfix = [](int, T raw) -> T { return raw; };      // xbuf holds x with zeros from row j on (phase A)
   // -- z1 = V^H v, z2 = W^H v: pair q = (which, cc) is done completely by the consumer warps of CTA G-1-q
   const int nf = p.nbp - 1 - c;      // finished columns cc in (c, nbp)
   if (nf > 0 && warp < NW) {
@@ -1084,7 +1093,7 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
           xv[k] = r < j ? ldcg_(p.xbuf + r) : zero_<T>();
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) fmac_((k & 1) ? s1 : s0, cv[k], xfix(r0 + k * NT, xv[k]));
+        for (int k = 0; k < 4; ++k) fmac_((k & 1) ? s1 : s0, cv[k], xv[k]);
       }
       s0 = warp_sum(add_(s0, s1));
       if (lane == 0) zr[warp] = s0;
@@ -1101,7 +1110,7 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
   tstamp(p, c, 13);
   // -- the tile engine: w_raw partials and v^H A v
   engine_run<T>(um, p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, p.vavunit, p.qctr + c, cta, G, p.use_tma != 0, ring,
-                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn, p.upc);
+                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn, p.upc, scalars_hook);
   return um.total;
 }
 
@@ -1326,6 +1335,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   p.zfin = ar.take<T>((size_t)2 * NBMAX);
   p.alpha_slot = ar.take<T>(16);
   p.scale_slot = ar.take<T>(16);
+  p.beta_slot = ar.take<double>(16);
   p.npart = ar.take<double>(grid);
   p.vavunit = ar.take<double>(nunits);
   p.barrier = ar.take<unsigned>(64 + NBMAX);      // barrier word + the per-column tile queue heads (one memset)
@@ -1372,6 +1382,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     p.etrace_off = (int64_t)n * TRSLOTS;
   }
   EIGB_CUDA_CHECK(cudaMemsetAsync(p.status, 0, sizeof(int), s));
+  EIGB_CUDA_CHECK(cudaMemsetAsync(p.xbuf, 0, ((size_t)n + 128) * sizeof(T), s));     // rows >= order must read as zero
   const bool coop = opts().trd_coop != 0;
   std::vector<GemmParams<T>> hp_all;          // multi-GPU: rank-2k parameter blocks, panel after panel
   std::vector<int> hp_off;
