@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libeigb200.so")
+LIB_PATH = os.environ.get("EIGB200_LIB_PATH") or os.path.join(HERE, "lib", "libeigb200.so")      # (override: debugging builds)
 
 _lib = None
 

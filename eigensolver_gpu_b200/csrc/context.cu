@@ -182,6 +182,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "trsm_leaf256")) { o.trsm_leaf256 = value; return 0; }
   if (!strcmp(name, "potrf_pb")) { if (value > 8192) return -1; o.potrf_pb = value; return 0; }
   if (!strcmp(name, "gemm_tma")) { o.gemm_tma = value; return 0; }
+  if (!strcmp(name, "gemm_tma_dbg")) { o.gemm_tma_dbg = value; return 0; }
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
   if (!strcmp(name, "trd_prefetch")) { if (value < -1 || value > 64) return -1; o.trd_prefetch = value; return 0; }
   if (!strcmp(name, "mg_switch_n")) { o.mg_switch_n = value; return 0; }

@@ -31,7 +31,6 @@ template <typename T> struct TCfg;
 template <> struct TCfg<double>  { static constexpr int BM = 128, BN = 64, WGM = 4, WGN = 2, DPE = 1, STAGES = 4; };
 template <> struct TCfg<double2> { static constexpr int BM = 64,  BN = 64, WGM = 2, WGN = 4, DPE = 2, STAGES = 3; };
 
-struct TmaMaps { CUtensorMap a[2], b[2]; };
 
 template <typename T>
 struct TmaArgs {
@@ -41,6 +40,7 @@ struct TmaArgs {
   double alpha, beta;
   int mode, real_diag, diag_off;
   const int* colmap;
+  int dbg;                 // debugging aid (option gemm_tma_dbg): 1 no early refill, 2 proxy fence before releasing a stage
 };
 
 __device__ __forceinline__ unsigned s_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -96,7 +96,13 @@ __device__ __forceinline__ int elem_off(int x, int k) {
 }
 
 template <typename T, bool AK, bool BK>
-__global__ void __launch_bounds__(NTH, 2) gemm_tma_kernel(const __grid_constant__ TmaMaps maps, const TmaArgs<T> p) {
+__global__ void __launch_bounds__(NTH, 2) gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
+                                                          const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+                                                          const __grid_constant__ TmaArgs<T> p) {
+  // Every tensor map is a kernel parameter of its own and every parameter is __grid_constant__ (no struct of maps, no
+  // run-time index into one): a build that passed the maps as one struct next to a plain by-value argument block gave
+  // wrong products now and then on long solves (n >= 10240), reproducibly per build and gone with this signature --
+  // see DESIGN.md ("TMA-fed GEMM": what went wrong).
   using C_ = TCfg<T>;
   constexpr int BM = C_::BM, BN = C_::BN, WGM = C_::WGM, WGN = C_::WGN, DPE = C_::DPE, STAGES = C_::STAGES;
   constexpr bool CPLX = is_cplx<T>::value;
@@ -134,13 +140,15 @@ __global__ void __launch_bounds__(NTH, 2) gemm_tma_kernel(const __grid_constant_
     unsigned char* Bs = As + A_BYTES;
     if (lane == 0) mb_expect_tx(&full[s], (unsigned)STAGE_BYTES);
     __syncwarp();
+    const CUtensorMap* ma = seg ? &map_a1 : &map_a0;
+    const CUtensorMap* mb = seg ? &map_b1 : &map_b0;
     if (lane < NBA) {
-      if constexpr (A_KMAJ) tma_load(As + lane * BOXA, &maps.a[seg], k0 * DPE + 16 * lane, m0, &full[s]);
-      else                  tma_load(As + lane * BOXA, &maps.a[seg], m0 * DPE + 16 * lane, k0, &full[s]);
+      if constexpr (A_KMAJ) tma_load(As + lane * BOXA, ma, k0 * DPE + 16 * lane, m0, &full[s]);
+      else                  tma_load(As + lane * BOXA, ma, m0 * DPE + 16 * lane, k0, &full[s]);
     } else if (lane < NBA + NBB) {
       const int b = lane - NBA;
-      if constexpr (B_KMAJ) tma_load(Bs + b * BOXB, &maps.b[seg], k0 * DPE + 16 * b, n0, &full[s]);
-      else                  tma_load(Bs + b * BOXB, &maps.b[seg], n0 * DPE + 16 * b, k0, &full[s]);
+      if constexpr (B_KMAJ) tma_load(Bs + b * BOXB, mb, k0 * DPE + 16 * b, n0, &full[s]);
+      else                  tma_load(Bs + b * BOXB, mb, n0 * DPE + 16 * b, k0, &full[s]);
     }
   };
   // k-tile j >= STAGES reuses the stage of k-tile j - STAGES: every warp must have released it
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(NTH, 2) gemm_tma_kernel(const __grid_constant_
     const int jn = kt + STAGES - 1;
     bool pending = false;
     if (warp == 0 && jn < KT) {
-      if (jn < STAGES || stage_free(jn, false)) issue(jn); else pending = true;
+      if (jn < STAGES || (!(p.dbg & 1) && stage_free(jn, false))) issue(jn); else pending = true;
     }
     mb_wait(&full[s], (unsigned)(kt / STAGES) & 1u);
     const unsigned char* As = smem + (size_t)s * STAGE_BYTES;
@@ -234,6 +242,7 @@ __global__ void __launch_bounds__(NTH, 2) gemm_tma_kernel(const __grid_constant_
           }
       }
     }
+    if (p.dbg & 2) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncwarp();
     if (lane == 0) mb_arrive(&empty[s]);              // this warp is done with the stage
     if (pending) { stage_free(jn, true); issue(jn); }
@@ -321,7 +330,7 @@ int launch_tma(cudaStream_t s, const GemmParams<T>& p) {
     EIGB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     once.done();
   }
-  TmaMaps maps;
+  struct { CUtensorMap a[2], b[2]; } maps;
   memset(&maps, 0, sizeof(maps));
   for (int seg = 0; seg < p.nseg; ++seg) {
     const int K = p.K[seg];
@@ -342,12 +351,13 @@ int launch_tma(cudaStream_t s, const GemmParams<T>& p) {
   a.sa[0] = p.sa[0]; a.sa[1] = p.sa[1]; a.sb[0] = p.sb[0]; a.sb[1] = p.sb[1];
   a.C = p.C; a.ldc = p.ldc; a.alpha = p.alpha; a.beta = p.beta;
   a.mode = p.mode; a.real_diag = p.real_diag; a.diag_off = p.diag_off; a.colmap = p.colmap;
+  a.dbg = opts().gemm_tma_dbg;
   if (a.KT0 == 0 && a.KT1 > 0) {              // keep segment 0 non-empty (the kernel maps k-tiles [0, KT0) to segment 0)
     maps.a[0] = maps.a[1]; maps.b[0] = maps.b[1];
     a.KT0 = a.KT1; a.KT1 = 0; a.sa[0] = a.sa[1]; a.sb[0] = a.sb[1];
   }
   dim3 grid(cdiv(p.M, C_::BM), cdiv(p.N, C_::BN), 1);
-  kern<<<grid, NTH, SMEM, s>>>(maps, a);
+  kern<<<grid, NTH, SMEM, s>>>(maps.a[0], maps.b[0], maps.a[1], maps.b[1], a);
   EIGB_LAUNCH_CHECK();
   return 0;
 }

@@ -24,6 +24,7 @@ struct Options {
   int trd_prefetch = 0; // tiles per CTA prefetched into L2 during phase A (-1: 256 KB worth, 0: off -- no gain measured)
   int hegst_hb = 0;     // block size of the reduction to standard form (0: 2048 for n >= 4096, else 1024)
   int gemm_tma = 1;     // host-parameter GEMMs on the TMA-fed kernel (0: cp.async kernel everywhere)
+  int gemm_tma_dbg = 0; // debugging aid for the TMA-fed kernel (bit 0: no early stage refill, bit 1: proxy fence before a stage release)
   int potrf_pb = 0;     // Cholesky: block-row height of the look-ahead variant (0: 192 complex / 256 real; < 0: plain recursion)
   int trsm_leaf256 = 1; // solves with a finished factor: 256x256 inverted diagonal blocks applied by the GEMM kernel
   int trd_l2keep_mb = 32; // tile engine: MB of the trailing matrix (its top tile rows) kept in L2 with evict_last; 0: no hints
