@@ -103,3 +103,44 @@ def test_hegst_large_blocks_match_lapack(cplx):
     c = np.triu(np.array(S.to_host(ad)))
     cr = np.triu(lapack.hegst(a, u))
     assert np.abs(c - cr).max() <= 50 * n * metrics.EPS * np.abs(cr).max()
+
+
+def test_tma_gemm_equals_cpasync_gemm_on_a_long_reduction():
+    """Regression for round 2's TMA incident ("TMA-fed GEMM: what went wrong"): hegst at n = 10240 with 2048-wide
+    blocks is several hundred back-to-back GEMM launches with long k loops; the TMA-fed kernel and the cp.async kernel
+    accumulate in the same order, so the two reductions must agree BITWISE"""
+    from eigensolver_gpu_b200 import stages as S
+    from eigensolver_gpu_b200._lib import load
+    lib = load()
+    n = 10240
+    t = torch.rand((n, n), dtype=torch.float64, device="cuda")
+    bm = t @ t.T / n + torch.eye(n, dtype=torch.float64, device="cuda")
+    del t
+    g = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    am = (g + g.T) / 2
+    del g
+    outs = []
+    try:
+        assert lib.eigb200_set_option(b"hegst_hb", 2048) == 0
+        for tma in (1, 0, 1):
+            assert lib.eigb200_set_option(b"gemm_tma", tma) == 0
+            u = bm.clone()
+            assert S.potrf(u) == 0
+            outs.append((torch.tril(u), torch.tril(S.hegst(am.clone(), u))))
+    finally:
+        lib.eigb200_set_option(b"gemm_tma", 1)
+        lib.eigb200_set_option(b"hegst_hb", 0)
+    for k in (0, 2):
+        assert torch.equal(outs[k][0], outs[1][0]) and torch.equal(outs[k][1], outs[1][1])
+
+
+def test_dsygvdx_n12288_gates():
+    """an order between the benchmarked ones (the first size at which round 2's TMA incident showed)"""
+    from eigensolver_gpu_b200 import api
+    n, m = 12288, 1536
+    a0, b0 = bench.make_inputs(torch, n, False, "C", 7)
+    A, B = a0.clone(), b0.clone()
+    info, w, z, ws = api.solve_generalized(A, B, 1, m, skip_host_copy=True)
+    assert info == 0
+    del A, B
+    _gates(a0, b0, w, z, m)
