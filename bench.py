@@ -300,8 +300,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="eigb200", choices=["eigb200", "reference", "cusolver"])
-    ap.add_argument("--n", type=int, default=8192)
-    ap.add_argument("--m", type=int, default=None)
+    ap.add_argument("--n", "--order", dest="n", type=int, default=8192, help="matrix order (--order under torchrun: its parser rejects --n as ambiguous)")
+    ap.add_argument("--m", "--wanted", dest="m", type=int, default=None, help="number of eigenpairs il=1..m (default: all)")
     ap.add_argument("--dtype", default="z", choices=["z", "d"])
     ap.add_argument("--ref-n", type=int, default=2048, help="order of the bounded CPU sample")
     ap.add_argument("--ref-budget-s", type=float, default=600.0, help="reference arm: time budget for ONE solve of the real order")

@@ -1431,9 +1431,19 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     if (p.P > 1) {
       p.seq_base = M.seq;
       M.seq += (unsigned long long)nbp;
-      // the panel's columns are current only on the rank that owns this tile column: broadcast them
-      if (M.hook) M.hook(p.i0, nbp, (p.i0 / TB) % M.P);
-      else if (mg_bcast_columns(s, A, lda, p.i0, nbp, (p.i0 / TB) % M.P, (int)sizeof(T)) != 0) return -1;
+      // the panel's columns are current only on the rank that owns this tile column: broadcast them.  So is column
+      // i0-1 (owned by the previous tile column's rank): the panel's last product (order i0) runs on the raw column, and
+      // its consumers correct the partial sums with the STORED column i0-1 and diagonal element (phase A of c = -1)
+      const int own = (p.i0 / TB) % M.P, own1 = p.i0 > 0 ? ((p.i0 - 1) / TB) % M.P : 0;
+      if (M.hook) {
+        M.hook(p.i0, nbp, own);
+        if (p.i0 > 0) M.hook(p.i0 - 1, 1, own1);
+      } else {
+        if (mg_group(true) != 0) return -1;
+        int rcb = mg_bcast_columns(s, A, lda, p.i0, nbp, own, (int)sizeof(T));
+        if (rcb == 0 && p.i0 > 0) rcb = mg_bcast_columns(s, A, lda, p.i0 - 1, 1, own1, (int)sizeof(T));
+        if (mg_group(false) != 0 || rcb != 0) return -1;
+      }
     }
     prof_begin(PROF_PANEL, s);
     EIGB_CUDA_CHECK(cudaMemsetAsync(p.barrier, 0, (64 + NBMAX) * sizeof(unsigned), s));
