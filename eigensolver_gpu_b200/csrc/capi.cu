@@ -57,6 +57,9 @@ int eigb200_mg_config(int rank, int world, void** wbufs, void** flags, long long
   for (int q = 0; q < world; ++q) { M.wbuf[q] = wbufs ? wbufs[q] : nullptr; M.flags[q] = flags ? (unsigned long long*)flags[q] : nullptr; }
   M.hook = (panel_hook_t)panel_hook;
   M.active = world > 1;
+  // every word of this rank's exchange buffer starts "unset" (sytrd.cu, multi-GPU exchange); the caller synchronises the
+  // ranks before the first solve
+  if (world > 1 && M.wbuf[rank]) EIGB_CUDA_CHECK(cudaMemset(M.wbuf[rank], 0xFF, (size_t)wbuf_bytes));
   return 0;
 }
 int eigb200_mg_unique_id(char* id128) {

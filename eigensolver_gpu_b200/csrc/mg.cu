@@ -108,8 +108,9 @@ void mg_column_range(int ncols, int world, int rank, int& c0, int& c1) {
   c1 = (int)(b1 * align < ncols ? b1 * align : ncols);
 }
 
-// flags per source rank for order <= n: one per 32-row group of the exchanged vector + one for v^H A v (+ slack)
-int mg_flag_stride(int n) { return (n + 31) / 32 + 8; }
+// flags per source rank for order <= n: one per (CTA, 32-row group of the CTA's rows) + one for v^H A v; the rows are dealt
+// to G <= 256 CTAs in blocks of R = roundup8(ceil(n / G)) rows, so G * ceil(R / 32) <= (n + 39 G) / 32
+int mg_flag_stride(int n) { return (n + 31) / 32 + 328; }
 
 int mg_unique_id(char* id128) {
   NcclApi* N = nccl_api();
@@ -174,7 +175,7 @@ int mg_ensure_exchange(cudaStream_t s, int n) {
   const size_t fbytes = (size_t)M.P * fstride * sizeof(unsigned long long);
   EIGB_CUDA_CHECK(cudaMalloc(&w, (size_t)need));
   EIGB_CUDA_CHECK(cudaMalloc(&f, fbytes));
-  EIGB_CUDA_CHECK(cudaMemset(w, 0, (size_t)need));
+  EIGB_CUDA_CHECK(cudaMemset(w, 0xFF, (size_t)need));      // every word "unset" (sytrd.cu, multi-GPU exchange)
   EIGB_CUDA_CHECK(cudaMemset(f, 0, fbytes));
   struct Handles { cudaIpcMemHandle_t hw, hf; } mine;
   EIGB_CUDA_CHECK(cudaIpcGetMemHandle(&mine.hw, w));

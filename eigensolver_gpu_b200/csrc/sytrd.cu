@@ -22,8 +22,9 @@
 //    deterministic whatever CTA ran a unit, no FP64 atomics (the reference's results depend on atomicAdd ordering).
 //  * w^H v is obtained algebraically (v^H A v - 2 Re(z1^H z2)), which removes a third barrier per column.
 //  * the same panel code runs down to column 1, so no separate unblocked 32x32 kernel is needed.
-//  * MG variant: tile columns distributed 1-D block-cyclically over P GPUs, partial w exchanged through
-//    peer-mapped buffers with flag signalling inside the kernel (phase C).
+//  * MG variant: tile columns distributed 1-D block-cyclically over P GPUs; phase A of the next column reduces the local
+//    partial sums of its rows, delivers them to the same CTA of every peer (stores into peer-mapped buffers over NVLink,
+//    one release flag per 32-row group) and adds the peers' shares in rank order: no extra phase, no third barrier.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "stages.cuh"
@@ -44,7 +45,6 @@ constexpr int NW = NT / 32;
 constexpr int NTT = NT + 32;  // + one TMA producer warp
 constexpr int NWT = NTT / 32;
 constexpr int NBMAX = 128;    // max panel width
-constexpr int AW = 8;         // warps that split the per-row work in phase C (multi-GPU)
 constexpr int TRSLOTS = 16;    // globaltimer stamps per column when tracing
 
 // Ring of tile stages filled by TMA.  One stage = a 64x64 tile + the x slices of the tile's rows and columns.
@@ -85,7 +85,7 @@ struct TrdP {
   // multi-GPU (1-D block-cyclic distribution of the 64-wide tile columns of the trailing matrix over P ranks)
   int rank, P;                 // P == 1: single GPU
   T* peer_w[8];                // peer_w[q] = rank q's exchange buffer [P][2][wstride] (peer-mapped, NVLink)
-  unsigned long long* peer_flag[8];   // peer_flag[q] = rank q's arrival flags [P sources][fstride]: one per 32-row group + [fstride-1] for v^H A v
+  unsigned long long* peer_flag[8];   // peer_flag[q] = rank q's arrival flags [P sources][fstride]: one per (CTA, 32-row group) + [fstride-1] for v^H A v
   int fstride;                 // flags per source rank
   int64_t wstride;             // elements per exchange slot (>= n + 2)
   unsigned long long seq_base; // sequence number of this panel's first column (flags are monotonic)
@@ -664,13 +664,27 @@ __device__ __forceinline__ T gather_partials(const T* Pd, const T* Pt, int64_t l
 }
 
 // ---- multi-GPU exchange helpers ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+// The exchanged words validate themselves: a slot holds the all-ones bit pattern (a NaN no computation produces) until the
+// sender's plain 8-byte stores land; the reader polls the data words (relaxed system-scope loads served by L2) and puts
+// the pattern back after use.  No flags and no system-scope fences (measured at ~4 us each on NVLink) on the critical path.
+__device__ __forceinline__ bool unset_(double v) { return __double_as_longlong(v) == -1ll; }
+__device__ __forceinline__ bool unset_(double2 v) { return unset_(v.x) || unset_(v.y); }
+template <typename T> __device__ __forceinline__ T unset_value();
+template <> __device__ __forceinline__ double unset_value<double>() { return __longlong_as_double(-1ll); }
+template <> __device__ __forceinline__ double2 unset_value<double2>() { return mkz(__longlong_as_double(-1ll), __longlong_as_double(-1ll)); }
+__device__ __forceinline__ double ld_poll(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;\n" :: "l"(p), "l"(v) : "memory");
+__device__ __forceinline__ double2 ld_poll(const double2* p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double shfl_(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double2 shfl_(double2 v, int src) {
+  return mkz(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
 }
 // sequence number of the exchange that follows the product of panel column c
 template <typename T>
@@ -736,7 +750,7 @@ __global__ void pad_copy_kernel(const T* x, int n, T* xpad, int npad) {
 //     V/W loop; the results travel through shared memory.
 template <typename T, bool MG>
 __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc& cd, const ColDesc& cdn,
-                        const CUtensorMap* tmap) {
+                        const CUtensorMap* tmap, int units_prev) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
   const int nbp = p.nbp;
@@ -745,6 +759,7 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
   const int cprev = c + 1;
   const bool have_prev = (cprev <= nbp - 1) && (jp >= 1);
   const bool mg = MG && p.P > 1;
+  const int Pn = mg ? p.P : 1, rk = mg ? p.rank : 0;
   PhaseASmem<T>& S = sm.u.a;
   const unsigned long long seqp = have_prev ? col_seq(p, cprev) : 0ull;
   const unsigned parp = (unsigned)(seqp & 1ull);
@@ -758,24 +773,8 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
   const int rbeg = cta * R;
   const int rend = nrows < rbeg + R ? nrows : rbeg + R;
   const int ngrp = rend > rbeg ? (rend - rbeg + 31) >> 5 : 0;
-  if (mg && have_prev) {
-    // wait until every rank has delivered what this CTA reads of the previous column's exchange: the 32-row groups that
-    // cover its rows, the group of row j (scalar warp) and v^H A v -- one flag per (source rank, group), no grid barrier
-    // on the sending side
-    const int gb = rbeg >> 5, ge = rend > rbeg ? (rend - 1) >> 5 : gb - 1;      // groups [gb, ge] (exchange groups are 32-aligned)
-    const int nown = ge - gb + 1;
-    const int nwait = (nown + 2) * p.P;
-    for (int idx = tid; idx < nwait; idx += NTT) {
-      const int q = idx % p.P, k = idx / p.P;
-      const int fi = k < nown ? gb + k : (k == nown ? (j >> 5) : p.fstride - 1);
-      const unsigned long long* fl = p.peer_flag[p.rank] + (int64_t)q * p.fstride + fi;
-      unsigned long long spins = 0;
-      while (ld_acquire_sys(fl) < seqp) {
-        if (++spins > (1ull << 25)) { atomicExch(p.status, 78); __trap(); }
-      }
-    }
-    __syncthreads();
-  }
+  // multi-GPU: the rows are dealt to the CTAs in the same way on every rank (R depends on the order and the grid only), so
+  // CTA i of rank q delivers its rows' partial sums to CTA i of every other rank
   const int gcs = ngrp <= 1 ? 0 : (ngrp == 2 ? 1 : 2);
   const int GC = 1 << gcs, wpgs = 4 - gcs, WPG = 1 << wpgs;
   const int grp = warp >> wpgs, sub = warp & (WPG - 1);        // warp 16: grp == GC -> no row work
@@ -807,9 +806,8 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
             a2[k] = mul_(scale_p, sub_(ldcg_(p.zfin + NBMAX + cc), scale_(conj_(a4[k]), beta_p)));
           }
         }
-        // partial-sum slots of row j (or the P exchange slots)
+        // partial-sum slots of row j (multi-GPU: the P exchange slots, after sync #1)
         T wj = zero_<T>();
-        double vx = 0.0;
         if (!mg) {
           const int ndj = cd.ndj, nsj = cd.nsj, Ij = j >> 6;
           for (int q0 = lane; q0 < nsj; q0 += 128) {
@@ -823,9 +821,6 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
 #pragma unroll
             for (int k = 0; k < 4; ++k) wj = add_(wj, v[k]);
           }
-        } else if (lane < p.P) {
-          wj = ldcg_(ex_slot(p, p.rank, lane, parp) + j);
-          vx = real_(ldcg_(ex_slot(p, p.rank, lane, parp) + p.wstride - 1));
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -844,15 +839,32 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
         }
         zz = warp_sum(zz);
         part = warp_sum(part);
-        const T wj_raw = warp_sum(wj);            // (A x)(j)
-        wj = mul_(scale_p, sub_(wj_raw, from_real<T>(beta_p * ajj_p)));    // (A v)(j) = scale * ((A x)(j) - beta A(j,j))
-        vx = warp_sum(vx);
+        T wj_raw = warp_sum(wj);                  // (A x)(j)
         __syncthreads();                          // (#1) workers' shares of x~^H A x~ are in dscal
-        double vv = vx;
+        double vv = 0.0;
         if (!mg) {
 #pragma unroll
           for (int w = 0; w < NW; ++w) vv += sm.dscal[w];
+        } else {
+          // row j's partial sums and the v^H A v shares of all ranks (this rank's own included: every rank adds the same P
+          // values in the same order, so the replicated panel stays bitwise identical across the ranks)
+          T wq = zero_<T>();
+          double vq = 0.0;
+          if (lane < p.P) {
+            const T* slot = ex_slot(p, p.rank, lane, parp);
+            T vqt;
+            unsigned long long spins = 0;
+            do {
+              wq = ld_poll(slot + p.wstride - 2);
+              vqt = ld_poll(slot + p.wstride - 1);
+              if (++spins > (1ull << 24)) { atomicExch(p.status, 78); __trap(); }
+            } while (unset_(wq) || unset_(vqt));
+            vq = real_(vqt);
+          }
+          wj_raw = zero_<T>();
+          for (int q = 0; q < p.P; ++q) { wj_raw = add_(wj_raw, shfl_(wq, q)); vv += __shfl_sync(0xffffffffu, vq, q); }
         }
+        wj = mul_(scale_p, sub_(wj_raw, from_real<T>(beta_p * ajj_p)));    // (A v)(j) = scale * ((A x)(j) - beta A(j,j))
         vv += beta_p * (beta_p * ajj_p - 2.0 * real_(wj_raw));     // x~^H A x~ from x^H A x
         vv *= abs2_(scale_p);                     // v^H A v = |scale|^2 x~^H A x~
         // rho = v^H A v - 2 Re(z1^H z2), alpha' = -1/2 |tau|^2 rho, W(j, c+1) = tau (w_j - part) + alpha' (v(j) = 1)
@@ -895,9 +907,9 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
     }
     const T scale_w = have_prev ? ldcg_(p.scale_slot) : zero_<T>();
     if (have_prev) {
-      if (round == 0 && !mg) {
-        // this thread's share of the per-unit v^H A v slots
-        const int total = cd.total;
+      if (round == 0) {
+        // this thread's share of the per-unit v^H A v slots (multi-GPU: of this rank's units)
+        const int total = mg ? units_prev : cd.total;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0;
         if (tid < total) v0 = __ldcg(p.vavunit + tid);
         if (tid + NT < total) v1 = __ldcg(p.vavunit + tid + NT);
@@ -907,37 +919,37 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
         if (lane == 0) sm.dscal[warp] = vs;
       }
       if (rv) {
-        if (!mg) {
-          // partial-sum slots of row r: direct J = I+1 .. Tn-1, then bands k = 0 .. I/Cp; this warp takes every WPG-th
-          const int I = r >> 6;
-          const int nd = Tn - (I + 1);
-          const int nt = ((I * cd.rcpC) >> 16) + 1;
-          const int64_t step = (int64_t)p.ldp << wpgs;
-          {
-            const T* ptr = p.Pd + (int64_t)(I + 1 + sub) * p.ldp + r;
-            int cnt = nd > sub ? (nd - sub + WPG - 1) >> wpgs : 0;
-            for (; cnt > 0; cnt -= 8) {
-              T v[8];
+        // partial-sum slots of row r: direct J = I+1 .. Tn-1 (multi-GPU: the owned ones, J = rank mod P), then bands
+        // k = 0 .. I/Cp (multi-GPU: only when this rank owns tile column I); this warp takes every WPG-th
+        const int I = r >> 6;
+        int J0 = I + 1;
+        if (mg) J0 += ((rk - J0) % Pn + Pn) % Pn;
+        const int nd = J0 < Tn ? (Tn - J0 + Pn - 1) / Pn : 0;
+        const int nt = (!mg || I % Pn == rk) ? ((I * cd.rcpC) >> 16) + 1 : 0;
+        {
+          const int64_t step = ((int64_t)p.ldp * Pn) << wpgs;
+          const T* ptr = p.Pd + (int64_t)(J0 + sub * Pn) * p.ldp + r;
+          int cnt = nd > sub ? (nd - sub + WPG - 1) >> wpgs : 0;
+          for (; cnt > 0; cnt -= 8) {
+            T v[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] = cnt > k ? ldcg_(ptr + k * step) : zero_<T>();
-              ptr += 8 * step;
-              wr = add_(wr, add_(add_(add_(v[0], v[1]), add_(v[2], v[3])), add_(add_(v[4], v[5]), add_(v[6], v[7]))));
-            }
+            for (int k = 0; k < 8; ++k) v[k] = cnt > k ? ldcg_(ptr + k * step) : zero_<T>();
+            ptr += 8 * step;
+            wr = add_(wr, add_(add_(add_(v[0], v[1]), add_(v[2], v[3])), add_(add_(v[4], v[5]), add_(v[6], v[7]))));
           }
-          {
-            const T* ptr = p.Pt + (int64_t)sub * p.ldp + r;
-            int cnt = nt > sub ? (nt - sub + WPG - 1) >> wpgs : 0;
-            for (; cnt > 0; cnt -= 4) {
-              const T v0 = ldcg_(ptr);
-              const T v1 = cnt > 1 ? ldcg_(ptr + step) : zero_<T>();
-              const T v2 = cnt > 2 ? ldcg_(ptr + 2 * step) : zero_<T>();
-              const T v3 = cnt > 3 ? ldcg_(ptr + 3 * step) : zero_<T>();
-              ptr += 4 * step;
-              wr = add_(wr, add_(add_(v0, v1), add_(v2, v3)));
-            }
+        }
+        {
+          const int64_t step = (int64_t)p.ldp << wpgs;
+          const T* ptr = p.Pt + (int64_t)sub * p.ldp + r;
+          int cnt = nt > sub ? (nt - sub + WPG - 1) >> wpgs : 0;
+          for (; cnt > 0; cnt -= 4) {
+            const T v0 = ldcg_(ptr);
+            const T v1 = cnt > 1 ? ldcg_(ptr + step) : zero_<T>();
+            const T v2 = cnt > 2 ? ldcg_(ptr + 2 * step) : zero_<T>();
+            const T v3 = cnt > 3 ? ldcg_(ptr + 3 * step) : zero_<T>();
+            ptr += 4 * step;
+            wr = add_(wr, add_(add_(v0, v1), add_(v2, v3)));
           }
-        } else {
-          for (int q = sub; q < p.P; q += WPG) wr = add_(wr, ldcg_(ex_slot(p, p.rank, q, parp) + r));
         }
       }
     }
@@ -951,6 +963,36 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
           pw[k] = ldcg_(p.W + r + (int64_t)cc * p.ldw);
         }
       }
+    }
+    T wloc = zero_<T>();                          // multi-GPU: this rank's complete partial sum of row r (sub == 0 warps)
+    if (mg && have_prev) {
+      // combine the WPG slices of a row group, then deliver the 32 sums to every other rank (plain stores over NVLink into
+      // the peers' exchange buffers); CTA 0 / warp 0 also delivers this rank's v^H A v
+      if (round == 0 && cta == 0 && warp == 0 && lane < p.P) {
+        // the scalar words of the other parity were read by all CTAs two grid barriers ago: mark them unset again
+        T* slot = ex_slot(p, p.rank, lane, parp ^ 1u);
+        slot[p.wstride - 2] = unset_value<T>(); slot[p.wstride - 1] = unset_value<T>();
+      }
+      S.ared[(warp * 32 + lane) * 2] = wr;
+      tstamp(p, c, 8);
+      consumer_barrier();
+      if (sub == 0) {
+        for (int w = 0; w < WPG; ++w) wloc = add_(wloc, S.ared[(((grp << wpgs) + w) * 32 + lane) * 2]);
+        if (rv) {
+          for (int q = 0; q < p.P; ++q) if (q != p.rank) ex_slot(p, q, p.rank, parp)[r] = wloc;
+          // (row j is read by the scalar warps of all CTAs of all ranks: a word of its own, this rank's copy included)
+          if (r == j) for (int q = 0; q < p.P; ++q) ex_slot(p, q, p.rank, parp)[p.wstride - 2] = wloc;
+        }
+        if (round == 0 && cta == 0 && warp == 0 && lane < p.P) {
+          double vloc = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) vloc += sm.dscal[w];
+          ex_slot(p, lane, p.rank, parp)[p.wstride - 1] = from_real<T>(vloc);
+        }
+        tstamp(p, c, 6);
+      }
+      if (round > 0) consumer_barrier();          // ared is written again below (round 0: sync #1 separates the two uses)
+      wr = zero_<T>();
     }
     tstamp(p, c, 5);
     if (round == 0) __syncthreads();              // (#1) z1, z2, rowV, rowW are in shared memory
@@ -980,11 +1022,34 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
     tstamp(p, c, 9);
     __syncthreads();                              // (#2) also: the scalar warp's results
     tstamp(p, c, 10);
+    tstamp(p, c, 11);
     if (rv && sub == 0) {
       T u = zero_<T>(), t2s = zero_<T>();
       for (int w = 0; w < WPG; ++w) {
         const T* a2 = S.ared + (((grp << wpgs) + w) * 32 + lane) * 2;
         u = add_(u, a2[0]); t2s = add_(t2s, a2[1]);
+      }
+      if (mg && have_prev) {
+        // the other ranks' partial sums of this row, added in rank order (this rank's own share comes from registers);
+        // every word is polled until the sender's store has landed, then marked unset for the column after the next
+        T part[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) part[q] = (q < p.P && q != p.rank) ? ld_poll(ex_slot(p, p.rank, q, parp) + r) : zero_<T>();
+        unsigned long long spins = 0;
+        for (bool again = true; again;) {
+          again = false;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < p.P && q != p.rank && unset_(part[q])) { part[q] = ld_poll(ex_slot(p, p.rank, q, parp) + r); again = true; }
+          if (++spins > (1ull << 24)) { atomicExch(p.status, 79); __trap(); }
+        }
+        T wtot = zero_<T>();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q < p.P && q != p.rank) ex_slot(p, p.rank, q, parp)[r] = unset_value<T>();
+          if (q < p.P) wtot = add_(wtot, q == p.rank ? wloc : part[q]);
+        }
+        u = add_(u, mul_(S.s_scale, wtot));
       }
       if (have_prev) {
         const T tau_p = S.s_tau, scale_p = S.s_scale, wjfin = S.s_wj;
@@ -1114,77 +1179,6 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
   return um.total;
 }
 
-// Phase C (multi-GPU only): reduce this rank's partial sums to one vector w_p(0:j) and push it, together with the
-// local v^H A v, into the exchange buffer of EVERY rank (peer stores over NVLink).  Every 32-row group is signalled on its
-// own: the warp that pushed a group fences (system scope) and releases one flag per peer, so the receiving CTAs -- which
-// wait only for the groups they read -- need no grid barrier on this side.
-template <typename T>
-__device__ void phase_c(const TrdP<T>& p, int c, PanelSmem<T>& sm, int total_units) {
-  const int tid = threadIdx.x;
-  const int G = gridDim.x, cta = blockIdx.x;
-  const int j = p.i0 + c;
-  if (j <= 0) return;
-  const int Tn = (j + TB - 1) / TB, C = strip_len(j, G, p.P, p.upc);
-  const unsigned long long seq = col_seq(p, c);
-  const unsigned par = (unsigned)(seq & 1ull);
-  // groups of 32 rows are dealt to the CTAs, two at a time (warps 0-7 / 8-15); the AW warps of a half split the
-  // partial-sum slots of its group (L2-latency bound: four independent loads in flight per lane), its first warp
-  // combines and pushes the 32 values to every rank
-  const int lane = tid & 31, warp = tid >> 5;
-  const int half = warp >> 3, wq = warp & (AW - 1);
-  const int ngroups = (j + 31) / 32;
-  for (int g0 = cta; g0 < ngroups; g0 += 2 * G) {
-    const int g = g0 + half * G;
-    const bool gv = warp < 2 * AW && g < ngroups;
-    const int r = g * 32 + lane;
-    const bool rv = gv && r < j;
-    if (gv) {
-      const int I = (g * 32) / TB;
-      int J0 = I + 1;
-      J0 += ((p.rank - J0) % p.P + p.P) % p.P;               // first owned tile column >= I+1
-      const int nd = J0 < Tn ? (Tn - J0 + p.P - 1) / p.P : 0;  // direct slots J0, J0+P, ...
-      const int nt = (I % p.P == p.rank) ? I / C + 1 : 0;      // band slots of an owned tile column
-      T sacc = zero_<T>();
-      if (rv) {
-        for (int q0 = wq; q0 < nd + nt; q0 += 4 * AW) {
-          T v[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int q = q0 + k * AW;
-            const T* src = (q < nd) ? (p.Pd + (int64_t)(J0 + q * p.P) * p.ldp) : (p.Pt + (int64_t)(q - nd) * p.ldp);
-            v[k] = q < nd + nt ? ldcg_(src + r) : zero_<T>();
-          }
-          sacc = add_(sacc, add_(add_(v[0], v[1]), add_(v[2], v[3])));
-        }
-      }
-      sm.u.a.ared[warp * 32 + lane] = sacc;
-    }
-    __syncthreads();
-    if (gv && wq == 0) {
-      if (rv) {
-        T tot = zero_<T>();
-#pragma unroll
-        for (int w = 0; w < AW; ++w) tot = add_(tot, sm.u.a.ared[(half * AW + w) * 32 + lane]);
-        for (int q = 0; q < p.P; ++q) ex_slot(p, q, p.rank, par)[r] = tot;
-      }
-      __threadfence_system();
-      __syncwarp();
-      if (lane < p.P) st_release_sys(p.peer_flag[lane] + (int64_t)p.rank * p.fstride + g, seq);
-    }
-    __syncthreads();
-  }
-  if (cta == G - 1) {       // (the last CTA has the fewest groups)
-    double vv = 0.0;
-    for (int t = tid; t < total_units; t += NTT) vv += __ldcg(p.vavunit + t);
-    vv = block_sum<double>(vv, sm.dscal);
-    if (tid < p.P) {
-      ex_slot(p, tid, p.rank, par)[p.wstride - 1] = from_real<T>(vv);
-      __threadfence_system();
-      st_release_sys(p.peer_flag[tid] + (int64_t)p.rank * p.fstride + p.fstride - 1, seq);
-    }
-  }
-}
-
 template <typename T, bool MG>
 __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constant__ CUtensorMap tmap, TrdP<T> p) {
   extern __shared__ __align__(1024) unsigned char dyn_smem[];
@@ -1195,10 +1189,11 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
   if (threadIdx.x == NT) compute_desc(sm.cd[(p.nbp - 1) & 1], p.i0 + p.nbp - 1, gridDim.x, Pn, p.upc);
   ring_init(sm.full, sm.empty, RingCfg<T>::STAGES, rs);      // (CTA barrier inside)
   unsigned target = 0;
+  int units_prev = 0;                  // tile units of the previous product (multi-GPU: of this rank)
   auto stamp = [&](int c, int k) { tstamp(p, c, k); };
   for (int c = p.nbp - 1; c >= -1; --c) {
     if (c >= 0) stamp(c, 0);
-    phase_a<T, MG>(p, c, sm, sm.cd[(c + 1) & 1], sm.cd[c & 1], &tmap);
+    phase_a<T, MG>(p, c, sm, sm.cd[(c + 1) & 1], sm.cd[c & 1], &tmap, units_prev);
     if (c < 0) break;
     stamp(c, 1);
     target += gridDim.x;
@@ -1206,14 +1201,12 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
     stamp(c, 2);
     const bool spread = p.trace != nullptr && p.i0 + c == p.etrace_j && threadIdx.x == 0;   // per-CTA begin/end of phase B
     if (spread) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.trace[p.etrace_off + 512 + blockIdx.x] = t; }
-    const int total_units = phase_b<T, MG>(p, c, sm, ring, rs, &tmap, sm.cd[c & 1], &sm.cd[(c + 1) & 1]);
+    units_prev = phase_b<T, MG>(p, c, sm, ring, rs, &tmap, sm.cd[c & 1], &sm.cd[(c + 1) & 1]);
     if (spread) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.trace[p.etrace_off + 768 + blockIdx.x] = t; }
     stamp(c, 3);
     target += gridDim.x;
+    // (multi-GPU: the exchange of the partial sums is part of the next phase A -- per-group flags, no third barrier)
     grid_barrier(p.barrier, target, p.status, false, []() {});
-    if (MG && p.P > 1 && p.i0 + c > 0) {
-      phase_c<T>(p, c, sm, total_units);        // (signals per 32-row group: no third grid barrier)
-    }
     stamp(c, 4);
   }
 }
@@ -1222,7 +1215,7 @@ __global__ void __launch_bounds__(NTT, 1) phase_a_kernel(TrdP<T> p, int c) {
   __shared__ PanelSmem<T> sm;
   if (threadIdx.x == 0) compute_desc(sm.cd[0], p.i0 + c + 1, gridDim.x, 1, p.upc);
   __syncthreads();
-  phase_a<T, false>(p, c, sm, sm.cd[0], sm.cd[0], nullptr);
+  phase_a<T, false>(p, c, sm, sm.cd[0], sm.cd[0], nullptr, 0);
   __syncthreads();
   if (threadIdx.x == 0 && c >= 0) store_npart(p, sm);
 }
@@ -1368,7 +1361,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     if (p.wstride < (int64_t)n + 2) { set_last_error("hetrd: multi-GPU exchange buffer too small"); return -1; }
     for (int q = 0; q < M.P; ++q) { p.peer_w[q] = (T*)M.wbuf[q]; p.peer_flag[q] = M.flags[q]; }
     p.fstride = M.flag_stride;
-    if (p.fstride < (n + 31) / 32 + 2) { set_last_error("hetrd: multi-GPU flag array too small"); return -1; }
+    (void)p.fstride;      // (the arrival flags are no longer used: the exchanged words validate themselves)
     // parameter blocks of the per-tile-column rank-2k updates of ALL panels: built once, uploaded once (no host
     // synchronisation inside the panel loop)
     const size_t ntc = (size_t)(n / TB + 2);

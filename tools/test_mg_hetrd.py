@@ -44,14 +44,19 @@ if rank == 0:
 dist.barrier()
 a2 = a0.clone(); d2, e2, t2 = be.hetrd_dist(a2); torch.cuda.synchronize()
 if rank == 0:
-    buf = np.zeros(n * 5, dtype=np.uint64)
-    lib.eigb200_trace_read(buf.ctypes.data_as(C.c_void_p), n * 5)
+    NS = 16
+    buf = np.zeros(n * NS, dtype=np.uint64)
+    lib.eigb200_trace_read(buf.ctypes.data_as(C.c_void_p), n * NS)
     lib.eigb200_set_option(b"trd_trace", 0)
-    t = buf.reshape(n, 5).astype(np.float64)
-    for lo in range(n - 512, -1, -2048):
+    t = buf.reshape(n, NS).astype(np.float64)
+    def med(sl, a, b):
+        ok = (t[sl, a] > 0) & (t[sl, b] > 0)
+        return np.median((t[sl, b] - t[sl, a])[ok]) / 1e3 if ok.any() else float("nan")
+    for lo in range(n - 512, -1, -1024):
         sl = slice(max(lo, 1), lo + 512)
-        print(f" cols {sl.start:5d}-{sl.stop:5d}: phaseA {np.median(t[sl,1]-t[sl,0])/1e3:6.1f} us | wait1 {np.median(t[sl,2]-t[sl,1])/1e3:5.1f} | "
-              f"phaseB {np.median(t[sl,3]-t[sl,2])/1e3:6.1f} | barrier+phaseC+signal {np.median(t[sl,4]-t[sl,3])/1e3:6.1f} | total {np.median(t[sl,4]-t[sl,0])/1e3:6.1f}", flush=True)
+        print(f" cols {sl.start:5d}-{sl.stop:5d}: phaseA {med(sl,0,1):5.1f} us [gather {med(sl,0,8):4.1f} combine+stores {med(sl,8,6):4.1f} fence+flags {med(sl,6,5):4.1f} sync1 {med(sl,5,7):4.1f} "
+              f"VW {med(sl,7,9):4.1f} sync2 {med(sl,9,10):4.1f} flagwait {med(sl,10,11):4.1f} finish {med(sl,11,1):4.1f}] | wait1 {med(sl,1,2):5.1f} | "
+              f"phaseB {med(sl,2,3):6.1f} | wait2 {med(sl,3,4):5.1f} | total {med(sl,0,4):6.1f}", flush=True)
 # consistency across ranks (must be bitwise identical)
 buf = [torch.zeros_like(d2) for _ in range(dist.get_world_size())]
 dist.all_gather(buf, d2)
