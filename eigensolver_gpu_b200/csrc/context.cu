@@ -183,6 +183,7 @@ int set_option(const char* name, int value) {
   if (!strcmp(name, "potrf_pb")) { if (value > 8192) return -1; o.potrf_pb = value; return 0; }
   if (!strcmp(name, "gemm_tma")) { o.gemm_tma = value; return 0; }
   if (!strcmp(name, "gemm_tma_dbg")) { o.gemm_tma_dbg = value; return 0; }
+  if (!strcmp(name, "trd_ctab")) { o.trd_ctab = value != 0; return 0; }
   if (!strcmp(name, "trd_upc")) { if ((value & 255) < 1 || (value & 255) > 64 || (value >> 8) > 32) return -1; o.trd_upc = value; return 0; }
   if (!strcmp(name, "trd_prefetch")) { if (value < -1 || value > 64) return -1; o.trd_prefetch = value; return 0; }
   if (!strcmp(name, "mg_switch_n")) { o.mg_switch_n = value; return 0; }
@@ -205,6 +206,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "potrf_pb")) return o.potrf_pb;
   if (!strcmp(name, "gemm_tma")) return o.gemm_tma;
   if (!strcmp(name, "trd_upc")) return o.trd_upc;
+  if (!strcmp(name, "trd_ctab")) return o.trd_ctab;
   if (!strcmp(name, "trd_prefetch")) return o.trd_prefetch;
   if (!strcmp(name, "mg_switch_n")) return o.mg_switch_n;
   if (!strcmp(name, "mg_dist_min_n")) return o.mg_dist_min_n;

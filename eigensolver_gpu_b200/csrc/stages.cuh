@@ -21,6 +21,7 @@ struct Options {
                               // below, the look-ahead single-GPU factorization replicated on every rank is faster)
   int mg_gather_z = 1;    // multi-GPU driver: gather the eigenvector column blocks so that every rank holds Z(:, 1:m)
   int trd_upc = 3;      // tile engine: target number of tile units per CTA (strip length heuristic)
+  int trd_ctab = 1;     // tile engine: strip length from the host-built table (replay of the unit queue); 0: closed-form heuristic
   int trd_prefetch = 0; // tiles per CTA prefetched into L2 during phase A (-1: 256 KB worth, 0: off -- no gain measured)
   int hegst_hb = 0;     // block size of the reduction to standard form (0: 2048 for n >= 4096, else 1024)
   int gemm_tma = 1;     // host-parameter GEMMs on the TMA-fed kernel (0: cp.async kernel everywhere)

@@ -78,6 +78,7 @@ struct TrdP {
   int* status;
   int use_tma;                 // tiles staged through the TMA ring (needs 16-byte aligned columns)
   int upc;                     // target number of tile units per CTA (strip length heuristic)
+  const unsigned char* ctab;   // strip length per number of tile rows (host-built, tile::build_strip_table); nullptr: heuristic
   int keepI;                   // L2 residency: tile rows < keepI are loaded with evict_last (0: no cache hints)
   int npf;                     // tiles each CTA prefetches into L2 during phase A (0: off)
   int etrace_j; int64_t etrace_off;   // (profiling aid) per-CTA begin/end stamps of phase B for the product of order etrace_j
@@ -552,7 +553,8 @@ template <typename T, class XR, class PH>
 __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t lda, int n, const T* __restrict__ xsrc,
                            XR xfix, T* Pd, T* Pt, int64_t ldp, double* vavunit, unsigned* qctr, int cta, int G, bool tma,
                            T* ring, uint64_t* full, uint64_t* empty, TileMeta* meta, RingState& rs, EngineSmem<T>& es,
-                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc, int upc, PH producer_hook) {
+                           const CUtensorMap* tmap, ColDesc* next_cd, int jnext, int Pdesc, int upc, const unsigned char* ctab,
+                           PH producer_hook) {
   constexpr int S = RingCfg<T>::STAGES, NBOX = RingCfg<T>::NBOX, DPE = RingCfg<T>::DPE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int st = rs.stage;
@@ -613,7 +615,7 @@ __device__ void engine_run(const UnitMap& um, const T* __restrict__ A, int64_t l
     }
     if (issued < S) producer_hook();
     // idle from here on: derive the next product's descriptor while the consumers drain the ring
-    if (lane == 0 && next_cd != nullptr) compute_desc(*next_cd, jnext, G, Pdesc, upc);
+    if (lane == 0 && next_cd != nullptr) compute_desc(*next_cd, jnext, G, Pdesc, upc, ctab);
   } else {
     // ===================== consumer warps =====================
     ConsumerState<T> cs;
@@ -723,7 +725,7 @@ __global__ void __launch_bounds__(NTT, 1) hemv_tiles_kernel(const __grid_constan
   auto xfix = [n](int r, T raw) -> T { return r < n ? raw : zero_<T>(); };
   const UnitMap um = engine_prepare<T>(n, C, 0, 1, es);
   engine_run<T>(um, A, lda, n, xpad, xfix, Pd, Pt, ldp, vavunit, qctr, blockIdx.x, gridDim.x, tma != 0, ring, full, empty,
-                meta, rs, es, &tmap, nullptr, 0, 1, 6, []() {});
+                meta, rs, es, &tmap, nullptr, 0, 1, 6, nullptr, []() {});
 }
 template <typename T>
 __global__ void hemv_reduce_kernel(const T* Pd, const T* Pt, int64_t ldp, int n, int C, T* y) {
@@ -1175,7 +1177,7 @@ __device__ int phase_b(const TrdP<T>& p, int c, PanelSmem<T>& sm, T* ring, RingS
   tstamp(p, c, 13);
   // -- the tile engine: w_raw partials and v^H A v
   engine_run<T>(um, p.A, p.lda, j, p.xbuf, xfix, p.Pd, p.Pt, p.ldp, p.vavunit, p.qctr + c, cta, G, p.use_tma != 0, ring,
-                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn, p.upc, scalars_hook);
+                sm.full, sm.empty, sm.meta, rs, sm.u.e, tmap, next_cd, p.i0 + c - 1, Pn, p.upc, p.ctab, scalars_hook);
   return um.total;
 }
 
@@ -1186,7 +1188,7 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
   T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
   RingState rs;
   const int Pn = MG ? p.P : 1;
-  if (threadIdx.x == NT) compute_desc(sm.cd[(p.nbp - 1) & 1], p.i0 + p.nbp - 1, gridDim.x, Pn, p.upc);
+  if (threadIdx.x == NT) compute_desc(sm.cd[(p.nbp - 1) & 1], p.i0 + p.nbp - 1, gridDim.x, Pn, p.upc, p.ctab);
   ring_init(sm.full, sm.empty, RingCfg<T>::STAGES, rs);      // (CTA barrier inside)
   unsigned target = 0;
   int units_prev = 0;                  // tile units of the previous product (multi-GPU: of this rank)
@@ -1213,7 +1215,7 @@ __global__ void __launch_bounds__(NTT, 1) panel_coop_kernel(const __grid_constan
 template <typename T>
 __global__ void __launch_bounds__(NTT, 1) phase_a_kernel(TrdP<T> p, int c) {
   __shared__ PanelSmem<T> sm;
-  if (threadIdx.x == 0) compute_desc(sm.cd[0], p.i0 + c + 1, gridDim.x, 1, p.upc);
+  if (threadIdx.x == 0) compute_desc(sm.cd[0], p.i0 + c + 1, gridDim.x, 1, p.upc, p.ctab);
   __syncthreads();
   phase_a<T, false>(p, c, sm, sm.cd[0], sm.cd[0], nullptr, 0);
   __syncthreads();
@@ -1225,7 +1227,7 @@ __global__ void __launch_bounds__(NTT, 1) phase_b_kernel(const __grid_constant__
   __shared__ PanelSmem<T> sm;
   T* ring = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
   RingState rs;
-  if (threadIdx.x == NT) compute_desc(sm.cd[0], p.i0 + c, gridDim.x, 1, p.upc);
+  if (threadIdx.x == NT) compute_desc(sm.cd[0], p.i0 + c, gridDim.x, 1, p.upc, p.ctab);
   ring_init(sm.full, sm.empty, RingCfg<T>::STAGES, rs);
   phase_b<T, false>(p, c, sm, ring, rs, &tmap, sm.cd[0], &sm.cd[1]);
 }
@@ -1316,7 +1318,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   size_t bytes = (2 * pe + (size_t)n * nb + (size_t)n + 256 + (size_t)2 * NBMAX + 64) * sizeof(T) +
                  nunits * sizeof(double) + 4096 +
                  ((size_t)(n / TB + 2) * (size_t)(n / TB + 2) / 2 + 2 * (size_t)(n / TB + 2) + 16) * sizeof(GemmParams<T>) +
-                 (size_t)(2 * grid + 64) * sizeof(double) + 4096 + 16 * 256;
+                 (size_t)(2 * grid + 64) * sizeof(double) + 4096 + 16 * 256 + 2 * (Tnn + 2 + 256);
   void* scr = ctx_scratch(bytes);
   if (!scr) return -1;
   Arena ar(scr, c.scratch_bytes);
@@ -1353,6 +1355,30 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
   p.rank = 0; p.P = 1;
   GemmParams<T>* GP = nullptr;
   const bool dist = M.P > 1 && M.active;
+  // strip length per number of tile rows: replay of the unit queue on the host (cached per grid / rank count / type)
+  const unsigned char* ctab_1 = nullptr; const unsigned char* ctab_p = nullptr;
+  if (opts().trd_ctab) {
+    const int cmax = (p.upc >> 8) ? (p.upc >> 8) : 8;
+    const double ov = is_cplx<T>::value ? 0.5 : 1.0;       // per-unit cost in tile times (real tiles are half the size)
+    const int Pm = (M.P > 1 && M.active) ? M.P : 1;
+    for (int pass = 0; pass < (Pm > 1 ? 2 : 1); ++pass) {
+      const int Pt = pass == 0 ? 1 : Pm;
+      static std::vector<unsigned char> cache[2][9];
+      static int cache_key[2][9][2];
+      std::vector<unsigned char>& tab = cache[is_cplx<T>::value ? 1 : 0][Pt];
+      int* key = cache_key[is_cplx<T>::value ? 1 : 0][Pt];
+      if ((int)tab.size() < (int)Tnn + 2 || key[0] != grid || key[1] != cmax) {
+        tab.assign(Tnn + 2, 1);
+        tile::build_strip_table(grid, Pt, (int)Tnn + 1, cmax, ov, tab.data());
+        key[0] = grid; key[1] = cmax;
+      }
+      unsigned char* dt = ar.take<unsigned char>(Tnn + 2);
+      if (!dt) { set_last_error("hetrd: scratch arena too small"); return -1; }
+      EIGB_CUDA_CHECK(cudaMemcpyAsync(dt, tab.data(), Tnn + 2, cudaMemcpyHostToDevice, s));
+      (pass == 0 ? ctab_1 : ctab_p) = dt;
+    }
+  }
+  p.ctab = ctab_1;
   if (dist) {
     if (!opts().trd_coop) { set_last_error("hetrd: multi-GPU needs the cooperative panel kernel"); return -1; }
     if (nb != TB) { set_last_error("hetrd: multi-GPU needs trd_nb == 64 (panels aligned to the tile columns)"); return -1; }
@@ -1421,6 +1447,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
       else if (mg_bcast_columns(s, A, lda, hi, 0, -1, (int)sizeof(T)) != 0) return -1;
       p.P = 1; p.rank = 0;
     }
+    p.ctab = p.P > 1 ? ctab_p : ctab_1;
     if (p.P > 1) {
       p.seq_base = M.seq;
       M.seq += (unsigned long long)nbp;

@@ -39,11 +39,12 @@ EIGB_HD int strip_len(int n, int G, int P, int upc) {
 // the phase A that follows (c-1) and is derived one column ahead by a single thread that would otherwise idle
 // (the producer warp, after its last tile): integer divisions and square roots cost ~25 dependent instructions
 // each, and 17 warps repeating them on the critical path of every column was a measurable part of it.
-EIGB_HD void compute_desc(ColDesc& d, int j, int G, int P, int upc) {
+EIGB_HD void compute_desc(ColDesc& d, int j, int G, int P, int upc, const unsigned char* ctab = nullptr) {
   d.j = j;
   if (j <= 0) { d.Tn = 0; d.C = 1; d.rcpC = 65536; d.KB = 0; d.NF = 0; d.total = 0; d.R = 0; d.ndj = 0; d.nsj = 0; return; }
   const int Tn = (j + TB - 1) / TB;
-  const int C = strip_len(j, G, P, upc);
+  // strip length: from the host-built table (build_strip_table) when there is one, else the closed-form heuristic
+  const int C = ctab != nullptr ? (int)ctab[Tn] : strip_len(j, G, P, upc);
   d.Tn = Tn; d.C = C; d.rcpC = (65536 + C - 1) / C;
   d.KB = (Tn - 1) / C;
   d.NF = d.KB * Tn - C * (d.KB * (d.KB + 1) / 2);
@@ -122,6 +123,50 @@ struct UnitMap {
   }
 };
 
+
+// Host side: strip length per number of tile rows, chosen by replaying the unit queue.  The F units of a product all have
+// C tiles, so after them the CTAs stand at q or q+1 units; the D units (1..C tiles, in queue order) then go to the
+// earliest free CTA.  A unit costs its tiles plus `ov` tile times (descriptor, strip end).  The closed-form heuristic
+// (strip_len) leaves up to a unit of imbalance at the end of a column -- 10 us of a 50 us column on two ranks.
+inline void build_strip_table(int G, int P, int Tnmax, int cmax, double ov, unsigned char* out /* Tnmax + 1 entries */) {
+  out[0] = 1;
+  double* fin = new double[G];
+  for (int Tn = 1; Tn <= Tnmax; ++Tn) {
+    int bestC = 1; double best = 1e300;
+    for (int C = 1; C <= cmax; ++C) {
+      if ((Tn - 1) / C > MAXBANDS) continue;
+      double worst = 0.0;
+      for (int rank = 0; rank < P; ++rank) {
+        UnitMap um; um.Tn = Tn; um.C = C; um.rank = rank; um.P = P;
+        um.TnO = rank < Tn ? (Tn - rank + P - 1) / P : 0;
+        const int KB = UnitMap::num_bands(Tn, C);
+        long long NF = 0;
+        for (int k = 0; k < KB; ++k) NF += um.band_count(k);
+        const double u = C + ov;
+        const long long q = NF / G; const int rem = (int)(NF % G);
+        for (int i = 0; i < G; ++i) fin[i] = (double)(q + (i < rem ? 1 : 0)) * u;
+        // D units in queue order: P == 1 by decreasing size, P > 1 by increasing tile column
+        auto place = [&](int tiles) {
+          int im = 0;
+          for (int i = 1; i < G; ++i) if (fin[i] < fin[im]) im = i;
+          fin[im] += tiles + ov;
+        };
+        if (P == 1) {
+          for (int s = (C < Tn ? C : Tn) - 1; s >= 0; --s)
+            for (int J = s; J < Tn; J += C) place(s + 1);
+        } else {
+          for (int J = rank; J < Tn; J += P) place(J % C + 1);
+        }
+        double mk = 0.0;
+        for (int i = 0; i < G; ++i) if (fin[i] > mk) mk = fin[i];
+        if (mk > worst) worst = mk;
+      }
+      if (worst <= best) { best = worst; bestC = C; }      // ties: the longer strip
+    }
+    out[Tn] = (unsigned char)bestC;
+  }
+  delete[] fin;
+}
 
 }  // namespace tile
 }  // namespace eigb200

@@ -43,3 +43,8 @@ extern "C" void unitmap_desc(int j, int G, int P, int upc, int* out /* j,Tn,C,rc
   out[0] = d.j; out[1] = d.Tn; out[2] = d.C; out[3] = d.rcpC; out[4] = d.KB; out[5] = d.NF; out[6] = d.total;
   out[7] = d.R; out[8] = d.ndj; out[9] = d.nsj;
 }
+
+// strip-length table (tile::build_strip_table) for CPU tests
+extern "C" void unitmap_strip_table(int G, int P, int Tnmax, int cmax, double ov, unsigned char* out) {
+  build_strip_table(G, P, Tnmax, cmax, ov, out);
+}

@@ -81,3 +81,31 @@ def test_descriptor_matches_unit_map_and_slot_formulas(um, j, G):
     # the slots phase A reads for ANY row are exactly the ones the units write: direct (I, J) for J > I, band I / C
     written_direct = {(int(i), int(jc)) for u, i, jc, d in tiles if d == 0}
     assert written_direct == {(i, jc) for jc in range(tn) for i in range(jc)}
+
+
+def _replay(tn, c, rank, p, g, ov):
+    """list scheduling of the unit queue (the model behind tile::build_strip_table), in tile times"""
+    owned = list(range(rank, tn, p))
+    kb = (tn - 1) // c
+    nf = sum(1 for k in range(kb) for j in owned if j >= (k + 1) * c)
+    fin = [(nf // g + (1 if i < nf % g else 0)) * (c + ov) for i in range(g)]
+    sizes = [j % c + 1 for j in owned]
+    if p == 1:
+        sizes.sort(reverse=True)
+    for s in sizes:
+        i = fin.index(min(fin))
+        fin[i] += s + ov
+    return max(fin)
+
+
+@pytest.mark.parametrize("g,p,ov", [(148, 1, 0.5), (148, 2, 0.5), (148, 4, 1.0), (148, 8, 0.5), (7, 3, 0.5)])
+def test_strip_table_minimises_the_replayed_makespan(um, g, p, ov):
+    tnmax, cmax = 140, 8
+    tab = np.zeros(tnmax + 1, dtype=np.uint8)
+    um.unitmap_strip_table(g, p, tnmax, cmax, C.c_double(ov), tab.ctypes.data_as(C.c_void_p))
+    assert tab[0] == 1 and tab.min() >= 1 and tab.max() <= cmax
+    for tn in (1, 2, 5, 17, 64, 96, 124, 140):
+        cost = {c: max(_replay(tn, c, r, p, g, ov) for r in range(p)) for c in range(1, cmax + 1)}
+        best = min(cost.values())
+        assert abs(cost[int(tab[tn])] - best) < 1e-9, (tn, tab[tn], cost)
+        assert (tn - 1) // int(tab[tn]) <= 256

@@ -7,6 +7,10 @@ sys.path.insert(0, ".")
 from eigensolver_gpu_b200 import stages as S, multi_gpu as MG
 
 n = int(sys.argv[1]); cplx = sys.argv[2] == "z"
+from eigensolver_gpu_b200._lib import load as _load
+for kv in os.environ.get("EIGB_OPTS", "").split(","):          # e.g. EIGB_OPTS=trd_upc=1027,mg_switch_n=2048
+    if "=" in kv:
+        k, v = kv.split("="); assert _load().eigb200_set_option(k.encode(), int(v)) == 0, kv
 rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
