@@ -15,7 +15,7 @@ struct Options {
   int bt_nb = 128;      // back-transformation block (reference: 64, zheevd_gpu.F90:64)
   int symv_tma = 1;     // stage symv/hemv tiles through TMA (cp.async.bulk.tensor) when alignment allows
   int trd_coop = 1;     // persistent cooperative panel kernel (0: one launch per phase)
-  int mg_switch_n = 3072; // multi-GPU hetrd: below this trailing order all ranks continue replicated
+  int mg_switch_n = -1; // multi-GPU hetrd: below this trailing order all ranks continue replicated (-1: 3072 on 2 ranks, else 2048)
   int mg_dist_min_n = -1; // multi-GPU driver: distribute the tridiagonalization from this order on (-1: 6144 for 2 ranks, else 4096)
   int mg_potrf_min_n = 20000; // multi-GPU driver: distribute the Cholesky factorization from this order on (-1: always replicated;
                               // below, the look-ahead single-GPU factorization replicated on every rank is faster)

@@ -1440,7 +1440,7 @@ int hetrd_upper(cudaStream_t s, int n, T* A, int64_t lda, double* d, double* e, 
     // the first (rightmost) panel absorbs the remainder so that the others are aligned to nb
     if (hi > nb && (hi % nb) != 0) nbp = hi % nb;
     p.i0 = hi - nbp; p.nbp = nbp;
-    if (dist && p.P > 1 && hi <= opts().mg_switch_n) {
+    if (dist && p.P > 1 && hi <= (opts().mg_switch_n >= 0 ? opts().mg_switch_n : (M.P <= 2 ? 3072 : 2048))) {
       // small trailing matrix: the per-column exchange costs more than the tiles it saves.  Make the leading hi
       // columns current everywhere (owner = -1: "gather all tile columns") and finish replicated (deterministic).
       if (M.hook) M.hook(hi, 0, -1);

@@ -11,7 +11,7 @@ except Exception as e:
     print("no line:", e, open(sys.argv[1].replace(".json",".err")).read()[-800:])
 P
 }
-(timeout 900 python -m pytest tests/test_multi_gpu_gpu.py -m gpu -q -x -k "$N]" 2>&1 | tail -60) | tee gpurun_out/r02_mgtests_g${N}_$tag.log
+(timeout 900 python -m pytest tests/test_multi_gpu_gpu.py -m gpu -q -x -k "${TESTK:-$N]}" 2>&1 | tail -60) | tee gpurun_out/r02_mgtests_g${N}_$tag.log
 (timeout 400 $TR --steps 3 --warmup 2 > gpurun_out/r02_scale_z8192_g${N}_$tag.json 2> gpurun_out/r02_scale_z8192_g${N}_$tag.err); show gpurun_out/r02_scale_z8192_g${N}_$tag.json
 (timeout 400 $TR --dtype d --order 16384 --wanted 2048 --steps 2 --warmup 1 > gpurun_out/r02_scale_d16384_g${N}_$tag.json 2> gpurun_out/r02_scale_d16384_g${N}_$tag.err); show gpurun_out/r02_scale_d16384_g${N}_$tag.json
 if [ "$N" = "8" ]; then
