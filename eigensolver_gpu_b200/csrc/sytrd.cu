@@ -810,6 +810,31 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
         }
         // partial-sum slots of row j (multi-GPU: the P exchange slots, after sync #1)
         T wj = zero_<T>();
+        if (mg && cta == G - 1) {
+          // This rank's share of (A x)(j), delivered to every rank (its own copy included) by the scalar warp of the last
+          // CTA.  It must not come from the worker warp that owns row j: with more than four row groups per CTA (orders
+          // above ~19000) that warp reaches row j in a later round, i.e. after the CTA barrier at which the scalar warps
+          // -- this CTA's too -- wait for this very value.
+          const int Ij = j >> 6;
+          int J0 = Ij + 1;
+          J0 += ((rk - J0) % Pn + Pn) % Pn;
+          const int nd = J0 < Tn ? (Tn - J0 + Pn - 1) / Pn : 0;
+          const int nt = (Ij % Pn == rk) ? ((Ij * cd.rcpC) >> 16) + 1 : 0;
+          T wl = zero_<T>();
+          for (int q0 = lane; q0 < nd + nt; q0 += 128) {
+            T v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int q = q0 + 32 * k;
+              const T* src = (q < nd) ? (p.Pd + (int64_t)(J0 + q * Pn) * p.ldp) : (p.Pt + (int64_t)(q - nd) * p.ldp);
+              v[k] = q < nd + nt ? ldcg_(src + j) : zero_<T>();
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wl = add_(wl, v[k]);
+          }
+          wl = warp_sum(wl);
+          if (lane < p.P) ex_slot(p, lane, p.rank, parp)[p.wstride - 2] = wl;
+        }
         if (!mg) {
           const int ndj = cd.ndj, nsj = cd.nsj, Ij = j >> 6;
           for (int q0 = lane; q0 < nsj; q0 += 128) {
@@ -982,8 +1007,6 @@ __device__ void phase_a(const TrdP<T>& p, int c, PanelSmem<T>& sm, const ColDesc
         for (int w = 0; w < WPG; ++w) wloc = add_(wloc, S.ared[(((grp << wpgs) + w) * 32 + lane) * 2]);
         if (rv) {
           for (int q = 0; q < p.P; ++q) if (q != p.rank) ex_slot(p, q, p.rank, parp)[r] = wloc;
-          // (row j is read by the scalar warps of all CTAs of all ranks: a word of its own, this rank's copy included)
-          if (r == j) for (int q = 0; q < p.P; ++q) ex_slot(p, q, p.rank, parp)[p.wstride - 2] = wloc;
         }
         if (round == 0 && cta == 0 && warp == 0 && lane < p.P) {
           double vloc = 0.0;

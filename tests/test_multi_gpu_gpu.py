@@ -156,3 +156,46 @@ def test_c_abi_multi_gpu_driver(world, cplx, n, il, iu):
     assert np.array_equal(w_h, w) and np.array_equal(z_h, z)
     u = lapack.potrf(b)
     assert np.abs(np.triu(bout) - u).max() <= 100 * n * metrics.EPS * np.abs(u).max()
+
+
+def _worker_hetrd_large(rank, world, port, cplx, n, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from eigensolver_gpu_b200 import multi_gpu as MG, stages as S
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    g = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=gen)
+    if cplx:
+        g = torch.complex(g, torch.randn((n, n), dtype=torch.float64, device="cuda", generator=gen))
+    a0 = (g + g.conj().T).contiguous()
+    del g
+    an = float(a0.abs().sum(dim=0).max())
+    a1 = a0.clone()
+    d1, e1, _ = S.hetrd(a1)                      # single-GPU kernel, same input
+    del a1
+    be = MG.CudaStages()
+    be.dist_hetrd_min_n = lambda world: 0
+    d, e, tau = be.hetrd_dist(a0)
+    ds = [torch.zeros_like(d) for _ in range(world)]
+    dist.all_gather(ds, d)
+    same = all(torch.equal(ds[0], x) for x in ds)
+    if rank == 0:
+        out.put((float((d - d1).abs().max()), float((e.abs() - e1.abs()).abs().max()), same, an,
+                 bool(torch.isfinite(d).all() and torch.isfinite(e).all())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_distributed_tridiagonalization_many_row_groups(world):
+    """order above 148 * 128: every CTA owns more than four 32-row groups, phase A runs in two rounds and the last row's
+    partial sum is owned by a warp that reaches it only in the second one (a first version of the in-kernel exchange
+    deadlocked there -- found at N=32768 on 8 GPUs)"""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n = 19200
+    dd, de, same, an, finite = _spawn(_worker_hetrd_large, world, (False, n))
+    assert same and finite
+    assert dd <= 20 * n * metrics.EPS * an and de <= 20 * n * metrics.EPS * an
