@@ -459,9 +459,11 @@ def main():
             parity["family_R_last_timed_solve"] = parity_metrics(torch, a0, b0, last["w"], last["z"], m)
         del a0, b0
         last.clear()
+        A = B = None                 # (N=32768 complex: 16 GiB each; the generator below needs the room for its temporaries)
         torch.cuda.empty_cache()
         a0, b0 = make_inputs(torch, n, cplx, "C", 4321)
-        A.copy_(a0); B.copy_(b0)
+        torch.cuda.empty_cache()
+        A = a0.clone(); B = b0.clone()
         w, z = solve_device()
         if rank == 0:
             pc = parity_metrics(torch, a0, b0, w, z, m)
