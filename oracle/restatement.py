@@ -5,7 +5,8 @@ Every function follows the reference routine named in its docstring (file:line r
 are 1-based Fortran).  Pure-numpy BLAS-2/3 calls stand in for the cuBLAS calls of the reference; the
 host ?stedc call of the reference is LAPACK itself (oracle.lapack.stedc).
 
-Parity pinning: the reference ships no golden vectors; this restatement is pinned in
+Parity pinning -- PARITY UNPINNED in the task's sense: the reference ships no golden vectors or known-answer tests for
+this path and cannot be built or run here; as the strongest substitute this restatement is pinned in
 tests/test_oracle.py against the reference's own ground truth, LAPACK ?sygvd/?hegvd, and against the
 fixtures in tests/golden/.
 """
