@@ -39,16 +39,18 @@ int eigb200_set_option(const char* name, int value);
 int eigb200_get_option(const char* name);
 
 /* ---- multi-GPU (one process per GPU): 1-D block-cyclic distribution of the trailing matrix inside ?sytrd/?hetrd ----
- * mg_alloc: cudaMalloc + zero `bytes` and export a 64-byte CUDA IPC handle; mg_open: map a peer's allocation;
- * mg_config: rank/world (world <= 8), the exchange buffers and flag arrays of ALL ranks (own entries = local pointers),
- * the size of one exchange buffer (>= world*2*(n+2) elements) and a callback `void hook(int i0, int nbp, int owner)` that
- * must broadcast columns [i0, i0+nbp) of A from rank `owner` to all ranks on the library's stream (the caller owns the
- * communicator, e.g. NCCL through torch.distributed).  world == 1 switches the mode off. */
+ * Caller-owned communicator (the Python test harness): mg_alloc: cudaMalloc `bytes` and export a 64-byte CUDA IPC handle;
+ * mg_open: map a peer's allocation; mg_config: rank/world (world <= 8), the exchange buffers of ALL ranks (own entry = the
+ * local pointer; this rank's buffer is filled with 0xFF: every exchanged word starts "unset" and validates itself, see
+ * csrc/sytrd.cu), the size of one exchange buffer (>= world*2*(n+2) complex elements) and a callback
+ * `void hook(int i0, int nbp, int owner)` that must broadcast columns [i0, i0+nbp) of A from rank `owner` to all ranks on
+ * the library's stream.  The flag arrays are no longer used (kept in the signature; may be NULL).  The caller synchronises
+ * the ranks between mg_config and the first solve.  world == 1 switches the mode off. */
 int eigb200_mg_alloc(long long bytes, void** dptr, char* handle64);
 int eigb200_mg_open(const char* handle64, void** dptr);
 int eigb200_mg_config(int rank, int world, void** wbufs, void** flags, long long wbuf_bytes, void* panel_hook);
-/* size of one rank's flag array for order n (one flag per source rank and 32-row group); exchange buffers are always sized
- * for complex elements: wbuf_bytes = world * 2 * (n + 64) * 16 */
+/* size of one rank's (unused, see above) flag array for order n; exchange buffers are always sized for complex elements:
+ * wbuf_bytes = world * 2 * (n + 64) * 16 */
 int eigb200_mg_flag_bytes(int n, int world);
 /* Library-owned communicator (what a Fortran/MPI caller uses; the functions above remain for callers that own the
  * communicator themselves).  Rendezvous: rank 0 calls eigb200_mg_unique_id (ncclGetUniqueId), the caller distributes the
@@ -97,7 +99,9 @@ int eigb200_zhegvdx(int n, void* A_d, int lda, void* B_d, int ldb, void* Z_d, in
  * (replicated device inputs) and its own buffers.  On exit on every rank: B <- U, w(1:N), Z(:,1:m) (column blocks gathered
  * unless option "mg_gather_z" = 0), host copies as requested; A is destroyed in BOTH triangles (Z serves as workspace).
  * Partition: hegst / back-transform / final solve by right-hand-side columns, hetrd trailing matrix 1-D block-cyclic with the
- * per-column exchange inside the panel kernel over NVLink, potrf and stedc replicated.  world == 1: the single-GPU driver. */
+ * per-column exchange inside the panel kernel over NVLink (peer-mapped buffers, no NCCL call per column), the root merge of
+ * the divide & conquer by eigenvector columns, potrf by block columns from order 20000 on (replicated below, like the lower
+ * levels of the divide & conquer).  world == 1: the single-GPU driver. */
 int eigb200_dsygvdx_mg(int n, double* A_d, int lda, double* B_d, int ldb, double* Z_d, int ldz, int il, int iu,
                        double* w_d, double* work_d, int lwork, double* work_h, int lwork_h, int* iwork_h,
                        int liwork_h, double* Z_h, int ldz_h, double* w_h, int* info, int skip_host_copy);
